@@ -1,0 +1,226 @@
+/*
+ * gofpid_b200.h -- C ABI of libgofpid_b200.so: PyGOFPID's per-frame foreground-extraction
+ * hot path (blur -> foreground detection -> morphology -> blob creation) as hand-written
+ * CUDA for sm_100a.
+ *
+ * The reference (qbarthelemy/PyGOFPID v1.1.0) is pure Python and has no FFI of its own; the
+ * plug points this ABI replaces are the OpenCV calls of GOFPID.detect
+ * (pygofpid/pipeline.py:461-479), each cited on the entry point that replaces it.
+ * INTEGRATION.md shows the ctypes stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C, opaque handles, int status returns (0 = OK, negative = error); the message
+ *     of the last error on the calling thread is returned by gofpid_last_error();
+ *   - nothing throws or aborts; there is NO CPU fallback: without a CUDA device every
+ *     compute entry point returns GOFPID_ERR_CUDA;
+ *   - "d_" pointers are device pointers owned by the caller (e.g. torch tensors),
+ *     "h_" pointers are host pointers; pitches are in bytes;
+ *   - `stream` arguments are cudaStream_t passed as void* (NULL = legacy default stream);
+ *     device entry points are asynchronous on that stream unless stated otherwise;
+ *   - one handle is single-threaded; distinct handles may be driven from distinct host
+ *     threads.
+ */
+#ifndef GOFPID_B200_H
+#define GOFPID_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(GOFPID_BUILD)
+#define GOFPID_API __attribute__((visibility("default")))
+#else
+#define GOFPID_API
+#endif
+
+/* ---- status codes --------------------------------------------------------------- */
+#define GOFPID_OK 0
+#define GOFPID_ERR_INVALID (-1)     /* bad argument (maps to ValueError / KeyError upstream)  */
+#define GOFPID_ERR_CUDA (-2)        /* CUDA runtime error, or no CUDA device                  */
+#define GOFPID_ERR_UNSUPPORTED (-3) /* valid for OpenCV but outside what the kernels cover    */
+#define GOFPID_ERR_NOMEM (-4)
+#define GOFPID_ERR_OVERFLOW (-5)    /* more blobs / contour points than the handle's capacity */
+
+/* ---- enumerations --------------------------------------------------------------- */
+enum { GOFPID_BLUR_NONE = 0, GOFPID_BLUR_GAUSSIAN = 1, GOFPID_BLUR_BOX = 2 };
+enum { GOFPID_DETECT_FD = 0, GOFPID_DETECT_MOG2 = 1, GOFPID_DETECT_KNN = 2 };
+enum { GOFPID_MORPH_ERODE = 0, GOFPID_MORPH_DILATE = 1 };
+
+#define GOFPID_MAX_MORPH_OPS 8
+#define GOFPID_MAX_KSIZE 31 /* largest blur kernel side the fused kernel stages in smem */
+#define GOFPID_MAX_SE 31    /* largest structuring-element side                          */
+#define GOFPID_MOG2_NMIX 5
+#define GOFPID_KNN_NSAMPLES 7
+
+/* One morphology step: d['fun'](mask, d['kernel']) of pipeline.py:473-475.  `kernel` is a
+ * host pointer to kh*kw bytes, row-major; non-zero = member of the structuring element. */
+typedef struct gofpid_morph_op {
+    int32_t op; /* GOFPID_MORPH_ERODE | GOFPID_MORPH_DILATE */
+    int32_t kh, kw;
+    const uint8_t *kernel;
+} gofpid_morph_op;
+
+/* Parameterisation of one pipeline.  gofpid_config_default() fills the values the reference
+ * uses: GOFPID.__init__ defaults (pipeline.py:168-212) and OpenCV's subtractor defaults
+ * (pipeline.py:232,234). */
+typedef struct gofpid_config {
+    /* blur: pipeline.py:462-467.  NB the reference passes blur['borderType'] positionally, so
+     * for cv.GaussianBlur it is sigmaX (default 4.0); the border is always REFLECT_101.  */
+    int32_t blur_kind;
+    int32_t blur_kw, blur_kh;
+    double blur_sigma; /* Gaussian sigma; <= 0: derived from the kernel size as OpenCV does */
+
+    int32_t detector; /* pipeline.py:231-240 */
+
+    /* frame differencing: segmentation.py:36 */
+    double fd_threshold;
+
+    /* MOG2: cv.createBackgroundSubtractorMOG2() defaults */
+    int32_t mog2_history;
+    float mog2_var_threshold;     /* Tb  = 16  */
+    float mog2_var_threshold_gen; /* Tg  = 9   */
+    float mog2_background_ratio;  /* TB  = 0.9 */
+    float mog2_var_init, mog2_var_min, mog2_var_max; /* 15, 4, 75 */
+    float mog2_ct;                /* complexity reduction threshold 0.05 */
+
+    /* KNN: cv.createBackgroundSubtractorKNN() defaults */
+    int32_t knn_history;      /* 500 */
+    int32_t knn_k;            /* 2   */
+    float knn_dist2_threshold; /* 400 */
+    uint64_t knn_rng_seed;    /* state of the cv::RNG replica; 0 -> 0xffffffff (OpenCV default) */
+
+    /* shared by MOG2 and KNN */
+    int32_t detect_shadows; /* 1 */
+    int32_t shadow_value;   /* 127 */
+    float shadow_tau;       /* 0.5 */
+
+    /* morphology: pipeline.py:473-476 */
+    int32_t n_morph;
+    gofpid_morph_op morph[GOFPID_MAX_MORPH_OPS];
+
+    /* blob creation: pipeline.py:555-570 (area_min is hard-coded to 100 there) */
+    int32_t find_blobs;    /* 0: stop after the mask */
+    double blob_area_min;  /* keep contours with cv.contourArea >= this */
+    int32_t max_blobs;     /* capacity: connected components per frame  */
+    int32_t max_kept;      /* capacity: blobs that pass the area filter */
+    int32_t max_points;    /* capacity: contour points per frame        */
+} gofpid_config;
+
+/* One blob that passed the area filter (the device-side half of GOFPID._create_blob,
+ * pipeline.py:572-588).  The host forms m00 = a00/2, m10 = a10/6, m01 = a01/6 as
+ * cv.moments does (helpers.py:156,165); a00 keeps its sign (orientation of the trace). */
+typedef struct gofpid_blob {
+    int32_t first;              /* raster index y*W+x of the component's first pixel   */
+    int32_t x0, y0, x1, y1;     /* inclusive bounding box (== cv.boundingRect)         */
+    int32_t area_px;            /* pixel count of the 8-connected component            */
+    int32_t n_points;           /* contour length (CHAIN_APPROX_NONE)                  */
+    int32_t point_offset;       /* index of the first point in the frame's point pool  */
+    int64_t a00, a10, a01;      /* Green sums over the contour polygon (exact)         */
+} gofpid_blob;
+
+/* Per-frame result header of one camera stream. */
+typedef struct gofpid_frame_info {
+    int32_t n_components; /* 8-connected foreground components                         */
+    int32_t n_candidates; /* external components passing the bbox pre-filter           */
+    int32_t n_kept;       /* blobs in the output list                                  */
+    int32_t n_points;     /* contour points in the pool                                */
+    int32_t overflow;     /* bit0: components, bit1: kept blobs, bit2: points          */
+    int32_t frame_index;  /* 1-based count of frames this stream has processed         */
+    int32_t reserved[2];
+} gofpid_frame_info;
+
+typedef struct gofpid_pipeline gofpid_pipeline; /* opaque */
+
+/* ---- library ------------------------------------------------------------------- */
+GOFPID_API const char *gofpid_version(void);
+GOFPID_API const char *gofpid_last_error(void);
+GOFPID_API int gofpid_device_count(void);
+GOFPID_API void gofpid_config_default(gofpid_config *cfg);
+
+/* 8.8 fixed-point taps cv.GaussianBlur uses for u8 images (n odd, <= GOFPID_MAX_KSIZE). */
+GOFPID_API int gofpid_gaussian_taps_q8(int n, double sigma, uint16_t *h_taps);
+
+/* ---- pipeline: n_streams independent camera streams of identical shape ---------------- */
+/* Replaces GOFPID.initialize()'s detector factory (pipeline.py:231-240) plus the state that
+ * cv2 keeps inside the subtractor objects.  Allocates the structure-of-arrays model in HBM
+ * on `device`.  Frames are u8, C interleaved channels (1 or 3). */
+GOFPID_API int gofpid_pipeline_create(const gofpid_config *cfg, int H, int W, int C,
+                                      int n_streams, int device, gofpid_pipeline **out);
+GOFPID_API int gofpid_pipeline_destroy(gofpid_pipeline *p);
+/* Forget all temporal state (as re-creating the cv2 subtractor would). */
+GOFPID_API int gofpid_pipeline_reset(gofpid_pipeline *p);
+
+/* One time step for every stream: blur -> detect -> morphology -> blobs
+ * (GOFPID.detect, pipeline.py:461-479).  d_frames holds n_streams frames, `stream_stride`
+ * bytes apart, rows `pitch` bytes apart.  Asynchronous on `stream`; results stay in HBM
+ * until fetched. */
+GOFPID_API int gofpid_pipeline_process_device(gofpid_pipeline *p, const uint8_t *d_frames,
+                                              size_t pitch, size_t stream_stride, void *stream);
+/* Same, from host memory: copies the frames host->device (pinned staging when h_frames is
+ * pageable), runs the step, copies result headers + blob lists back and synchronises. */
+GOFPID_API int gofpid_pipeline_process_host(gofpid_pipeline *p, const uint8_t *h_frames,
+                                            size_t pitch, size_t stream_stride);
+
+/* Results of the last step (host copies; these synchronise with the pipeline's stream). */
+GOFPID_API int gofpid_pipeline_frame_info(gofpid_pipeline *p, int stream_idx,
+                                          gofpid_frame_info *h_info);
+/* Blobs in the reference's order (descending raster order of the first pixel) and their
+ * contour points as (x, y) int32 pairs.  Capacities are in records / points. */
+GOFPID_API int gofpid_pipeline_blobs(gofpid_pipeline *p, int stream_idx, gofpid_blob *h_blobs,
+                                     int blob_capacity, int32_t *h_points, int point_capacity,
+                                     int *n_blobs, int *n_points);
+/* foreground_mask_ of pipeline.py:476, (H, W) u8, to host or device memory. */
+GOFPID_API int gofpid_pipeline_mask(gofpid_pipeline *p, int stream_idx, uint8_t *dst,
+                                    size_t dst_pitch, int dst_is_device);
+/* Canonical labels: 0 = background, else 1 + raster index of the component's first pixel. */
+GOFPID_API int gofpid_pipeline_labels(gofpid_pipeline *p, int stream_idx, int32_t *dst,
+                                      size_t dst_pitch, int dst_is_device);
+/* Per-component statistics of the last frame (unordered): first, x0, y0, x1, y1, area_px
+ * as 6 int32 per component. */
+GOFPID_API int gofpid_pipeline_components(gofpid_pipeline *p, int stream_idx, int32_t *h_stats,
+                                          int capacity, int *n_components);
+
+/* Model state, for parity checks and checkpointing (cv2 hides it).  MOG2: dense arrays
+ * weight[H][W][5], var[H][W][5], mean[H][W][5][C] (f32) and nmodes[H][W] (u8), host memory. */
+GOFPID_API int gofpid_pipeline_mog2_model(gofpid_pipeline *p, int stream_idx, float *h_weight,
+                                          float *h_var, float *h_mean, uint8_t *h_nmodes);
+/* KNN: samples[H][W][21][C+1], idx[3][H][W], nxt[3][H][W] (u8), counters[3], RNG state. */
+GOFPID_API int gofpid_pipeline_knn_model(gofpid_pipeline *p, int stream_idx, uint8_t *h_samples,
+                                         uint8_t *h_idx, uint8_t *h_nxt, int32_t *h_counters,
+                                         uint64_t *rng_state);
+/* FD: the previous (blurred) frame, [H][W][C] u8; returns 1 through *valid once a frame has
+ * been seen. */
+GOFPID_API int gofpid_pipeline_fd_model(gofpid_pipeline *p, int stream_idx, uint8_t *h_prev,
+                                        int *valid);
+/* Mean number of live MOG2 modes per pixel of the last frame (feeds the algorithmic-bytes
+ * figure of the roofline). */
+GOFPID_API int gofpid_pipeline_mog2_mean_modes(gofpid_pipeline *p, double *mean_modes);
+
+/* Timing aid for bench.py: device time (ms, CUDA events on the pipeline's launch stream)
+ * spent in each stage kernel group during the last process call:
+ * [0] blur+detect, [1] morphology, [2] labelling+stats, [3] contours, [4] whole step. */
+GOFPID_API int gofpid_pipeline_set_profiling(gofpid_pipeline *p, int enabled);
+GOFPID_API int gofpid_pipeline_stage_ms(gofpid_pipeline *p, float *h_ms5);
+/* Number of kernels the last process call launched. */
+GOFPID_API int gofpid_pipeline_launch_count(gofpid_pipeline *p);
+
+/* ---- stage-level entry points (device buffers, used by the parity tests) ------------- */
+/* cv.GaussianBlur / cv.blur on u8, BORDER_REFLECT_101 (pipeline.py:463). */
+GOFPID_API int gofpid_blur_u8(const uint8_t *d_src, size_t src_pitch, uint8_t *d_dst,
+                              size_t dst_pitch, int H, int W, int C, int kind, int kw, int kh,
+                              double sigma, void *stream);
+/* Chain of cv.erode / cv.dilate, fused in shared memory (pipeline.py:473-475). */
+GOFPID_API int gofpid_morph_u8(const uint8_t *d_src, size_t src_pitch, uint8_t *d_dst,
+                               size_t dst_pitch, int H, int W, const gofpid_morph_op *ops,
+                               int n_ops, void *stream);
+/* 8-connected labelling of a u8 mask (non-zero = foreground) into canonical int32 labels. */
+GOFPID_API int gofpid_ccl_u8(const uint8_t *d_mask, size_t mask_pitch, int32_t *d_labels,
+                             size_t labels_pitch, int H, int W, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GOFPID_B200_H */

@@ -1,0 +1,184 @@
+// common.cuh -- shared declarations of libgofpid_b200 (sm_100a only).
+//
+// Internal interface between the translation units:
+//   detect.cu   fused blur + {frame differencing, MOG2, KNN} kernels, frame tick, cv::RNG fill
+//   morph.cu    fused erode/dilate chain
+//   blobs.cu    union-find labelling, component statistics, outer-border tracing
+//   pipeline.cu the C ABI of include/gofpid_b200.h
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/gofpid_b200.h"
+
+namespace gofpid {
+
+// ------------------------------------------------------------------ error plumbing
+void set_error(const char *fmt, ...);
+#define GOFPID_CUDA_TRY(expr)                                                              \
+    do {                                                                                   \
+        cudaError_t _e = (expr);                                                           \
+        if (_e != cudaSuccess) {                                                           \
+            gofpid::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e),      \
+                              __FILE__, __LINE__);                                         \
+            return GOFPID_ERR_CUDA;                                                        \
+        }                                                                                  \
+    } while (0)
+#define GOFPID_TRY(expr)                                                                   \
+    do {                                                                                   \
+        int _s = (expr);                                                                   \
+        if (_s != GOFPID_OK) return _s;                                                    \
+    } while (0)
+
+static inline size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
+
+// ------------------------------------------------------------------ geometry
+// Fused blur+detect kernels: a CTA owns a tile of (32*PX) x DET_TH pixels; thread (tx, ty)
+// owns PX consecutive pixels of one row.
+constexpr int DET_TH = 8;
+constexpr int DET_PX = 4;
+
+// BORDER_REFLECT_101, iterated for tiny images (cv2 BORDER_DEFAULT).
+__host__ __device__ inline int reflect101(int p, int len)
+{
+    if (len == 1) return 0;
+    while (p < 0 || p >= len) p = p < 0 ? -p : 2 * (len - 1) - p;
+    return p;
+}
+
+// ------------------------------------------------------------------ blur
+struct BlurParams {
+    int kind;       // GOFPID_BLUR_*
+    int kw, kh;     // kernel size (1 when kind == NONE)
+    int rx, ry;     // anchors kw/2, kh/2
+    int box_d, box_delta, box_scale; // box normalisation (see detect.cu)
+    uint16_t qx[GOFPID_MAX_KSIZE + 1];
+    uint16_t qy[GOFPID_MAX_KSIZE + 1];
+};
+int make_blur_params(int kind, int kw, int kh, double sigma, BlurParams *bp);
+int gaussian_taps_q8(int n, double sigma, uint16_t *q);
+
+struct FrameSrc {
+    const uint8_t *base;
+    size_t pitch;         // bytes between rows
+    size_t stream_stride; // bytes between streams
+};
+struct ImageU8 {
+    uint8_t *base;
+    size_t pitch;
+    size_t stream_stride;
+};
+
+// ------------------------------------------------------------------ per-frame scalars
+// Written on the device by tick_kernel at the start of every step so that a captured
+// CUDA graph can be replayed unchanged.
+struct FrameTick {
+    int32_t nframes;  // 1-based index of the frame being processed
+    // MOG2
+    float alphaT, alpha1, prune;
+    // KNN
+    int32_t knn_u[3];       // update periods uS, uM, uL
+    int32_t knn_counter[3]; // counters cS, cM, cL valid DURING the frame
+    int32_t knn_refresh[3]; // tier draws fresh next-update ticks this frame
+    uint64_t knn_rng_start;    // RNG state before this frame's fills
+    uint64_t knn_draw_off[3];  // draws before each refreshed tier's fill, within one stream
+    uint64_t knn_draws;        // draws one stream consumes this frame (all refreshed tiers)
+    uint64_t knn_rng;          // RNG state after this frame's fills (all streams)
+    // FD
+    int32_t fd_valid; // a previous frame exists
+};
+
+// ------------------------------------------------------------------ detector state
+struct Mog2Params {
+    float Tb, TB, Tg, varInit, varMin, varMax, tau;
+    int detectShadows, shadowVal, history;
+    float ct;
+};
+struct Mog2Model {
+    float *planes;        // per stream: weight[5], var[5], mean[5][C] planes of PW*H floats
+    uint8_t *nmodes;      // per stream: PW*H bytes
+    size_t plane_elems;   // PW*H
+    size_t stream_planes; // planes per stream = 10 + 5*C
+    int PW;               // row pitch in elements (multiple of 32)
+};
+struct KnnParams {
+    float Tb, tau;
+    int knn, detectShadows, shadowVal, history;
+};
+struct KnnModel {
+    uint8_t *samples;      // per stream: 21 planes of PW*H*(C+1) bytes
+    uint32_t *nxt;         // per stream: PW*H words (nxtS | nxtM<<8 | nxtL<<16)
+    uint16_t *idx;         // per stream: PW*H halfwords (idxS | idxM<<3 | idxL<<6)
+    uint8_t *fresh;        // per stream: 3 dense arrays of H*W bytes (RNG fills S, M, L)
+    size_t plane_elems;    // PW*H
+    int PW;
+};
+struct FdModel {
+    uint8_t *prev; // per stream: previous blurred frame, pitch PB bytes
+    size_t pitch, stream_stride;
+};
+
+// ------------------------------------------------------------------ launchers
+struct DetectLaunch {
+    int H, W, C, n_streams;
+    FrameSrc src;
+    BlurParams blur;
+    ImageU8 mask; // (H, W) u8 per stream, padded pitch (multiple of 128 bytes)
+    const FrameTick *tick;
+    cudaStream_t stream;
+};
+int launch_tick(FrameTick *tick, int detector, const Mog2Params &mp, const KnnParams &kp,
+                const int32_t *knn_u_table, int knn_table_len, const uint64_t *pow2tab, int H,
+                int W, int n_streams, cudaStream_t s);
+int launch_blur_only(const DetectLaunch &L, ImageU8 dst);
+int launch_fd(const DetectLaunch &L, FdModel model, int thr);
+int launch_mog2(const DetectLaunch &L, Mog2Model model, const Mog2Params &mp);
+int launch_knn(const DetectLaunch &L, KnnModel model, const KnnParams &kp,
+               const uint64_t *d_jump_table);
+int detect_launches_per_step(int detector);
+
+// morphology ------------------------------------------------------------------
+struct MorphRun { int8_t dy, dx; uint8_t len; uint8_t pad; }; // horizontal run of an SE row
+struct MorphOpDev {
+    int op;          // GOFPID_MORPH_*
+    int kh, kw, ay, ax;
+    int is_rect;     // every element set -> separable path
+    int run_begin, run_end; // slice of the run table
+};
+struct MorphPlan {
+    int n_ops;
+    MorphOpDev ops[GOFPID_MAX_MORPH_OPS];
+    int halo_l, halo_r, halo_t, halo_b; // accumulated over the chain
+    MorphRun *d_runs;                   // device copy of the run table
+    int n_runs;
+    int tile_w, tile_h;                 // output tile per CTA
+    size_t smem_bytes;
+};
+int morph_plan_create(const gofpid_morph_op *ops, int n_ops, MorphPlan *plan);
+void morph_plan_destroy(MorphPlan *plan);
+int launch_morph(const MorphPlan &plan, ImageU8 src, ImageU8 dst, int H, int W, int n_streams,
+                 cudaStream_t s);
+
+// blobs ------------------------------------------------------------------------
+struct BlobBuffers {
+    int32_t *labels;      // per stream: LP*H int32 (signed: >0 fg root value, <=0 bg class)
+    size_t labels_pitch;  // elements
+    size_t labels_stream; // elements between streams
+    int32_t *slot;        // per stream: LP*H int32, component slot of root pixels (sparse)
+    int32_t *comp;        // per stream: max_blobs * 8 int32 component records
+    gofpid_frame_info *info; // per stream
+    int32_t *cand;        // per stream: max_blobs candidate slots
+    gofpid_blob *kept;    // per stream: max_kept records
+    int32_t *points;      // per stream: max_points * 2 int32
+    int max_blobs, max_kept, max_points;
+    double area_min;
+};
+int launch_blobs(const BlobBuffers &B, ImageU8 mask, int H, int W, int n_streams,
+                 const FrameTick *tick, cudaStream_t s, int *n_launches);
+int launch_canonical_labels(const uint8_t *mask, size_t mask_pitch, const int32_t *labels, size_t LP,
+                            int32_t *out, size_t out_pitch_elems, int H, int W, cudaStream_t s);
+int launch_ccl_only(const uint8_t *d_mask, size_t mask_pitch, int32_t *d_labels,
+                    size_t labels_pitch_elems, int H, int W, cudaStream_t s);
+
+} // namespace gofpid

@@ -1,0 +1,809 @@
+// pipeline.cu -- the C ABI of include/gofpid_b200.h.
+//
+// A gofpid_pipeline owns, in HBM, everything cv2 keeps inside GOFPID's per-stream objects
+// (pipeline.py:231-240: the MOG2 / KNN subtractor or FrameDifferencing._model) for n_streams
+// independent camera streams of one shape, plus the intermediate mask / label / blob buffers
+// of the step.  One step = GOFPID.detect lines pipeline.py:461-479 for every stream.
+#include "common.cuh"
+
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include <algorithm>
+#include <new>
+#include <vector>
+
+namespace gofpid {
+
+static thread_local char g_error[512] = "";
+void set_error(const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_error, sizeof(g_error), fmt, ap);
+    va_end(ap);
+}
+
+} // namespace gofpid
+
+using namespace gofpid;
+
+struct gofpid_pipeline {
+    gofpid_config cfg;
+    std::vector<std::vector<uint8_t>> se_copies;
+    int H = 0, W = 0, C = 0, n_streams = 0, device = 0;
+    cudaStream_t stream = nullptr;     // own stream (process_host, fetches)
+    cudaStream_t last_stream = nullptr; // stream of the last process call
+    BlurParams blur;
+    Mog2Params mog2p;
+    KnnParams knnp;
+    int fd_thr = 0;
+
+    FrameTick *d_tick = nullptr;
+    uint8_t *d_mask[2] = {nullptr, nullptr};
+    size_t mask_pitch = 0, mask_stream = 0;
+    int final_mask = 0;
+
+    Mog2Model mog2 = {};
+    KnnModel knn = {};
+    FdModel fd = {};
+    int32_t *d_knn_table = nullptr;
+    int knn_table_len = 0;
+    uint64_t *d_pow2tab = nullptr;
+
+    MorphPlan morph = {};
+    BlobBuffers blobs = {};
+
+    // host-side staging
+    uint8_t *d_frames = nullptr;
+    size_t frames_pitch = 0, frames_stream = 0;
+    uint8_t *h_frames = nullptr; // pinned
+
+    // fetched results (pinned)
+    gofpid_frame_info *h_info = nullptr;
+    gofpid_blob *h_kept = nullptr;  // n_streams * max_kept
+    int32_t *h_points = nullptr;    // n_streams * max_points * 2
+    bool results_valid = false;     // host copies correspond to the last step
+    bool stepped = false;
+
+    bool profiling = false;
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    int launch_count = 0;
+};
+
+namespace {
+
+struct DeviceGuard {
+    int prev = -1;
+    bool ok = true;
+    explicit DeviceGuard(int dev)
+    {
+        if (cudaGetDevice(&prev) != cudaSuccess) { ok = false; return; }
+        if (prev != dev && cudaSetDevice(dev) != cudaSuccess) ok = false;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+
+#define GOFPID_GUARD(p)                                                             \
+    if (!(p)) { set_error("null pipeline handle"); return GOFPID_ERR_INVALID; }    \
+    DeviceGuard _guard((p)->device);                                                \
+    if (!_guard.ok) { set_error("cannot select CUDA device %d", (p)->device); return GOFPID_ERR_CUDA; }
+
+int check_stream_index(const gofpid_pipeline *p, int idx)
+{
+    if (idx < 0 || idx >= p->n_streams) {
+        set_error("stream index %d out of range [0, %d)", idx, p->n_streams);
+        return GOFPID_ERR_INVALID;
+    }
+    return GOFPID_OK;
+}
+
+uint64_t host_mulmod(uint64_t a, uint64_t b)
+{
+    const uint64_t m = (4164903690ULL << 32) - 1ULL;
+    return (uint64_t)(((unsigned __int128)a * b) % m);
+}
+
+// KNN update periods for frame n (cv::BackgroundSubtractorKNNImpl::apply)
+void knn_periods(long n, int history, int nsamples, int32_t *u)
+{
+    const long n2 = 2 * n;
+    const double lr = 1.0 / (double)(n2 < history ? n2 : history);
+    const int Ks = (int)(log(0.7) / log(1 - lr)) + 1;
+    const int Km = (int)(log(0.4) / log(1 - lr)) - Ks + 1;
+    const int Kl = (int)(log(0.1) / log(1 - lr)) - Ks - Km + 1;
+    u[0] = Ks / nsamples + 1;
+    u[1] = Km / nsamples + 1;
+    u[2] = Kl / nsamples + 1;
+}
+
+int alloc_zero(void **ptr, size_t bytes)
+{
+    GOFPID_CUDA_TRY(cudaMalloc(ptr, bytes ? bytes : 1));
+    GOFPID_CUDA_TRY(cudaMemset(*ptr, 0, bytes ? bytes : 1));
+    return GOFPID_OK;
+}
+
+int reset_state(gofpid_pipeline *p)
+{
+    FrameTick t;
+    memset(&t, 0, sizeof(t));
+    t.knn_rng = p->cfg.knn_rng_seed ? p->cfg.knn_rng_seed : 0xffffffffULL;
+    GOFPID_CUDA_TRY(cudaMemcpy(p->d_tick, &t, sizeof(t), cudaMemcpyHostToDevice));
+    const size_t npl = p->mog2.plane_elems;
+    if (p->cfg.detector == GOFPID_DETECT_MOG2) {
+        GOFPID_CUDA_TRY(cudaMemset(p->mog2.nmodes, 0, npl * p->n_streams));
+    } else if (p->cfg.detector == GOFPID_DETECT_KNN) {
+        const size_t pe = p->knn.plane_elems;
+        GOFPID_CUDA_TRY(cudaMemset(p->knn.samples, 0, pe * 21 * (p->C + 1) * p->n_streams));
+        GOFPID_CUDA_TRY(cudaMemset(p->knn.nxt, 0, pe * sizeof(uint32_t) * p->n_streams));
+        GOFPID_CUDA_TRY(cudaMemset(p->knn.idx, 0, pe * sizeof(uint16_t) * p->n_streams));
+    }
+    p->results_valid = false;
+    p->stepped = false;
+    return GOFPID_OK;
+}
+
+void free_all(gofpid_pipeline *p)
+{
+    cudaFree(p->d_tick);
+    cudaFree(p->d_mask[0]); cudaFree(p->d_mask[1]);
+    cudaFree(p->mog2.planes); cudaFree(p->mog2.nmodes);
+    cudaFree(p->knn.samples); cudaFree(p->knn.nxt); cudaFree(p->knn.idx); cudaFree(p->knn.fresh);
+    cudaFree(p->fd.prev);
+    cudaFree(p->d_knn_table); cudaFree(p->d_pow2tab);
+    morph_plan_destroy(&p->morph);
+    cudaFree(p->blobs.labels); cudaFree(p->blobs.slot); cudaFree(p->blobs.comp);
+    cudaFree(p->blobs.info); cudaFree(p->blobs.cand); cudaFree(p->blobs.kept); cudaFree(p->blobs.points);
+    cudaFree(p->d_frames);
+    if (p->h_frames) cudaFreeHost(p->h_frames);
+    if (p->h_info) cudaFreeHost(p->h_info);
+    if (p->h_kept) cudaFreeHost(p->h_kept);
+    if (p->h_points) cudaFreeHost(p->h_points);
+    for (auto &e : p->ev) if (e) cudaEventDestroy(e);
+    if (p->stream) cudaStreamDestroy(p->stream);
+}
+
+int build(gofpid_pipeline *p)
+{
+    const gofpid_config &cfg = p->cfg;
+    const int H = p->H, W = p->W, C = p->C, S = p->n_streams;
+    GOFPID_CUDA_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    for (auto &e : p->ev) GOFPID_CUDA_TRY(cudaEventCreate(&e));
+    GOFPID_TRY(make_blur_params(cfg.blur_kind, cfg.blur_kw, cfg.blur_kh, cfg.blur_sigma, &p->blur));
+
+    GOFPID_TRY(alloc_zero((void **)&p->d_tick, sizeof(FrameTick)));
+    p->mask_pitch = round_up((size_t)W, 128);
+    p->mask_stream = p->mask_pitch * H;
+    GOFPID_TRY(alloc_zero((void **)&p->d_mask[0], p->mask_stream * S));
+    GOFPID_TRY(alloc_zero((void **)&p->d_mask[1], p->mask_stream * S));
+
+    const int PW = (int)round_up((size_t)W, 32);
+    const size_t pe = (size_t)PW * H;
+    p->mog2.PW = PW; p->mog2.plane_elems = pe; p->mog2.stream_planes = 10 + 5 * C;
+    p->knn.PW = PW; p->knn.plane_elems = pe;
+    Mog2Params &mp = p->mog2p;
+    mp.Tb = cfg.mog2_var_threshold; mp.TB = cfg.mog2_background_ratio; mp.Tg = cfg.mog2_var_threshold_gen;
+    mp.varInit = cfg.mog2_var_init; mp.varMin = cfg.mog2_var_min; mp.varMax = cfg.mog2_var_max;
+    mp.tau = cfg.shadow_tau; mp.detectShadows = cfg.detect_shadows; mp.shadowVal = cfg.shadow_value;
+    mp.history = cfg.mog2_history; mp.ct = cfg.mog2_ct;
+    KnnParams &kp = p->knnp;
+    kp.Tb = cfg.knn_dist2_threshold; kp.tau = cfg.shadow_tau; kp.knn = cfg.knn_k;
+    kp.detectShadows = cfg.detect_shadows; kp.shadowVal = cfg.shadow_value; kp.history = cfg.knn_history;
+
+    if (cfg.detector == GOFPID_DETECT_MOG2) {
+        if (cfg.mog2_history < 1) { set_error("MOG2 history must be >= 1"); return GOFPID_ERR_INVALID; }
+        GOFPID_TRY(alloc_zero((void **)&p->mog2.planes, pe * p->mog2.stream_planes * sizeof(float) * S));
+        GOFPID_TRY(alloc_zero((void **)&p->mog2.nmodes, pe * S));
+    } else if (cfg.detector == GOFPID_DETECT_KNN) {
+        if (cfg.knn_history < 1) { set_error("KNN history must be >= 1"); return GOFPID_ERR_INVALID; }
+        GOFPID_TRY(alloc_zero((void **)&p->knn.samples, pe * 21 * (C + 1) * S));
+        GOFPID_TRY(alloc_zero((void **)&p->knn.nxt, pe * sizeof(uint32_t) * S));
+        GOFPID_TRY(alloc_zero((void **)&p->knn.idx, pe * sizeof(uint16_t) * S));
+        GOFPID_TRY(alloc_zero((void **)&p->knn.fresh, (size_t)H * W * 3 * S));
+        p->knn_table_len = (cfg.knn_history + 1) / 2 + 1;
+        std::vector<int32_t> tab((size_t)p->knn_table_len * 3, 1);
+        for (int n = 1; n < p->knn_table_len; n++)
+            knn_periods(n, cfg.knn_history, GOFPID_KNN_NSAMPLES, &tab[(size_t)n * 3]);
+        for (size_t i = 0; i < tab.size(); i++)
+            if (tab[i] < 1 || tab[i] > 255) {
+                set_error("KNN history %d gives an update period outside [1, 255]", cfg.knn_history);
+                return GOFPID_ERR_UNSUPPORTED;
+            }
+        GOFPID_CUDA_TRY(cudaMalloc(&p->d_knn_table, tab.size() * sizeof(int32_t)));
+        GOFPID_CUDA_TRY(cudaMemcpy(p->d_knn_table, tab.data(), tab.size() * sizeof(int32_t),
+                                   cudaMemcpyHostToDevice));
+        uint64_t pw[64];
+        pw[0] = 4164903690ULL;
+        for (int j = 1; j < 64; j++) pw[j] = host_mulmod(pw[j - 1], pw[j - 1]);
+        GOFPID_CUDA_TRY(cudaMalloc(&p->d_pow2tab, sizeof(pw)));
+        GOFPID_CUDA_TRY(cudaMemcpy(p->d_pow2tab, pw, sizeof(pw), cudaMemcpyHostToDevice));
+    } else if (cfg.detector == GOFPID_DETECT_FD) {
+        p->fd.pitch = round_up(round_up((size_t)W, 4) * C, 128);
+        p->fd.stream_stride = p->fd.pitch * H;
+        GOFPID_TRY(alloc_zero((void **)&p->fd.prev, p->fd.stream_stride * S));
+        p->fd_thr = (int)floor(cfg.fd_threshold);
+    } else {
+        set_error("Unknown method for foreground detection (%d)", cfg.detector);
+        return GOFPID_ERR_INVALID;
+    }
+
+    GOFPID_TRY(morph_plan_create(p->cfg.morph, p->cfg.n_morph, &p->morph));
+    p->final_mask = p->cfg.n_morph > 0 ? 1 : 0;
+
+    if (cfg.find_blobs) {
+        BlobBuffers &B = p->blobs;
+        B.max_blobs = cfg.max_blobs; B.max_kept = cfg.max_kept; B.max_points = cfg.max_points;
+        B.area_min = cfg.blob_area_min;
+        if (B.max_blobs < 1 || B.max_kept < 1 || B.max_points < 1) {
+            set_error("blob capacities must be positive");
+            return GOFPID_ERR_INVALID;
+        }
+        B.labels_pitch = round_up((size_t)W, 4);
+        B.labels_stream = B.labels_pitch * H;
+        if (B.labels_stream >= (size_t)0x7fffffff) { set_error("frame too large for int32 labels"); return GOFPID_ERR_UNSUPPORTED; }
+        GOFPID_TRY(alloc_zero((void **)&B.labels, B.labels_stream * sizeof(int32_t) * S));
+        GOFPID_TRY(alloc_zero((void **)&B.slot, B.labels_stream * sizeof(int32_t) * S));
+        GOFPID_TRY(alloc_zero((void **)&B.comp, (size_t)B.max_blobs * 8 * sizeof(int32_t) * S));
+        GOFPID_TRY(alloc_zero((void **)&B.info, sizeof(gofpid_frame_info) * S));
+        GOFPID_TRY(alloc_zero((void **)&B.kept, sizeof(gofpid_blob) * B.max_kept * S));
+        GOFPID_TRY(alloc_zero((void **)&B.points, sizeof(int32_t) * 2 * B.max_points * S));
+        GOFPID_CUDA_TRY(cudaMallocHost(&p->h_kept, sizeof(gofpid_blob) * B.max_kept * S));
+        GOFPID_CUDA_TRY(cudaMallocHost(&p->h_points, sizeof(int32_t) * 2 * B.max_points * S));
+    }
+    GOFPID_CUDA_TRY(cudaMallocHost(&p->h_info, sizeof(gofpid_frame_info) * S));
+    memset(p->h_info, 0, sizeof(gofpid_frame_info) * S);
+    return reset_state(p);
+}
+
+int run_step(gofpid_pipeline *p, const uint8_t *d_frames, size_t pitch, size_t stream_stride,
+             cudaStream_t s)
+{
+    const bool prof = p->profiling;
+    int launches = 0;
+    if (prof) GOFPID_CUDA_TRY(cudaEventRecord(p->ev[0], s));
+    GOFPID_TRY(launch_tick(p->d_tick, p->cfg.detector, p->mog2p, p->knnp, p->d_knn_table,
+                           p->knn_table_len, p->d_pow2tab, p->H, p->W, p->n_streams, s));
+    DetectLaunch L;
+    L.H = p->H; L.W = p->W; L.C = p->C; L.n_streams = p->n_streams;
+    L.src = FrameSrc{d_frames, pitch, stream_stride};
+    L.blur = p->blur;
+    L.mask = ImageU8{p->d_mask[0], p->mask_pitch, p->mask_stream};
+    L.tick = p->d_tick;
+    L.stream = s;
+    if (p->cfg.detector == GOFPID_DETECT_MOG2) GOFPID_TRY(launch_mog2(L, p->mog2, p->mog2p));
+    else if (p->cfg.detector == GOFPID_DETECT_KNN) GOFPID_TRY(launch_knn(L, p->knn, p->knnp, p->d_pow2tab));
+    else GOFPID_TRY(launch_fd(L, p->fd, p->fd_thr));
+    launches += detect_launches_per_step(p->cfg.detector);
+    if (prof) GOFPID_CUDA_TRY(cudaEventRecord(p->ev[1], s));
+    if (p->cfg.n_morph > 0) {
+        GOFPID_TRY(launch_morph(p->morph, L.mask, ImageU8{p->d_mask[1], p->mask_pitch, p->mask_stream},
+                                p->H, p->W, p->n_streams, s));
+        launches += 1;
+    }
+    if (prof) GOFPID_CUDA_TRY(cudaEventRecord(p->ev[2], s));
+    if (p->cfg.find_blobs) {
+        int nb = 0;
+        GOFPID_TRY(launch_blobs(p->blobs, ImageU8{p->d_mask[p->final_mask], p->mask_pitch, p->mask_stream},
+                                p->H, p->W, p->n_streams, p->d_tick, s, &nb));
+        launches += nb;
+    }
+    if (prof) GOFPID_CUDA_TRY(cudaEventRecord(p->ev[3], s));
+    p->launch_count = launches;
+    p->last_stream = s;
+    p->results_valid = false;
+    p->stepped = true;
+    return GOFPID_OK;
+}
+
+// Brings the per-stream headers, kept blobs and contour points of the last step to the host.
+int fetch_results(gofpid_pipeline *p)
+{
+    if (p->results_valid) return GOFPID_OK;
+    if (!p->stepped) { set_error("no frame has been processed yet"); return GOFPID_ERR_INVALID; }
+    cudaStream_t s = p->last_stream;
+    const int S = p->n_streams;
+    if (!p->cfg.find_blobs) {
+        GOFPID_CUDA_TRY(cudaStreamSynchronize(s));
+        FrameTick t;
+        GOFPID_CUDA_TRY(cudaMemcpy(&t, p->d_tick, sizeof(t), cudaMemcpyDeviceToHost));
+        for (int z = 0; z < S; z++) { memset(&p->h_info[z], 0, sizeof(gofpid_frame_info)); p->h_info[z].frame_index = t.nframes; }
+        p->results_valid = true;
+        return GOFPID_OK;
+    }
+    GOFPID_CUDA_TRY(cudaMemcpyAsync(p->h_info, p->blobs.info, sizeof(gofpid_frame_info) * S,
+                                    cudaMemcpyDeviceToHost, s));
+    GOFPID_CUDA_TRY(cudaStreamSynchronize(s));
+    bool any = false;
+    for (int z = 0; z < S; z++) {
+        const int nk = std::min(p->h_info[z].n_kept, p->blobs.max_kept);
+        const int np = std::min(p->h_info[z].n_points, p->blobs.max_points);
+        if (nk > 0) {
+            GOFPID_CUDA_TRY(cudaMemcpyAsync(p->h_kept + (size_t)z * p->blobs.max_kept,
+                                            p->blobs.kept + (size_t)z * p->blobs.max_kept,
+                                            sizeof(gofpid_blob) * nk, cudaMemcpyDeviceToHost, s));
+            any = true;
+        }
+        if (np > 0) {
+            GOFPID_CUDA_TRY(cudaMemcpyAsync(p->h_points + (size_t)z * p->blobs.max_points * 2,
+                                            p->blobs.points + (size_t)z * p->blobs.max_points * 2,
+                                            sizeof(int32_t) * 2 * np, cudaMemcpyDeviceToHost, s));
+            any = true;
+        }
+    }
+    if (any) GOFPID_CUDA_TRY(cudaStreamSynchronize(s));
+    p->results_valid = true;
+    return GOFPID_OK;
+}
+
+} // namespace
+
+// =====================================================================================
+// library
+// =====================================================================================
+extern "C" {
+
+GOFPID_API const char *gofpid_version(void) { return "gofpid_b200 0.1.0 (sm_100a)"; }
+GOFPID_API const char *gofpid_last_error(void) { return g_error; }
+
+GOFPID_API int gofpid_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+GOFPID_API void gofpid_config_default(gofpid_config *cfg)
+{
+    if (!cfg) return;
+    memset(cfg, 0, sizeof(*cfg));
+    cfg->blur_kind = GOFPID_BLUR_GAUSSIAN; // pipeline.py:171-175
+    cfg->blur_kw = cfg->blur_kh = 3;
+    cfg->blur_sigma = 4.0; // cv.BORDER_DEFAULT (4) lands in sigmaX: pipeline.py:463-467
+    cfg->detector = GOFPID_DETECT_MOG2;
+    cfg->fd_threshold = 5.0;
+    cfg->mog2_history = 500;
+    cfg->mog2_var_threshold = 16.0f;
+    cfg->mog2_var_threshold_gen = 9.0f;
+    cfg->mog2_background_ratio = 0.9f;
+    cfg->mog2_var_init = 15.0f;
+    cfg->mog2_var_min = 4.0f;
+    cfg->mog2_var_max = 75.0f;
+    cfg->mog2_ct = 0.05f;
+    cfg->knn_history = 500;
+    cfg->knn_k = 2;
+    cfg->knn_dist2_threshold = 400.0f;
+    cfg->knn_rng_seed = 0;
+    cfg->detect_shadows = 1;
+    cfg->shadow_value = 127;
+    cfg->shadow_tau = 0.5f;
+    cfg->n_morph = 0; // the caller supplies structuring elements (pipeline.py:177-186)
+    cfg->find_blobs = 1;
+    cfg->blob_area_min = 100.0; // pipeline.py:555
+    cfg->max_blobs = 1 << 16;
+    cfg->max_kept = 4096;
+    cfg->max_points = 1 << 20;
+}
+
+GOFPID_API int gofpid_gaussian_taps_q8(int n, double sigma, uint16_t *h_taps)
+{
+    if (!h_taps) { set_error("null output"); return GOFPID_ERR_INVALID; }
+    const int rc = gaussian_taps_q8(n, sigma, h_taps);
+    if (rc) set_error("Gaussian kernel size must be odd and in [1, %d], got %d", GOFPID_MAX_KSIZE, n);
+    return rc;
+}
+
+GOFPID_API int gofpid_pipeline_create(const gofpid_config *cfg, int H, int W, int C, int n_streams,
+                                      int device, gofpid_pipeline **out)
+{
+    if (!cfg || !out) { set_error("null argument"); return GOFPID_ERR_INVALID; }
+    *out = nullptr;
+    if (H <= 0 || W <= 0 || n_streams <= 0) {
+        set_error("invalid geometry H=%d W=%d n_streams=%d", H, W, n_streams);
+        return GOFPID_ERR_INVALID;
+    }
+    if (C != 1 && C != 3) {
+        set_error("frames must have 1 or 3 channels, got %d", C);
+        return GOFPID_ERR_UNSUPPORTED;
+    }
+    if (cfg->n_morph < 0 || cfg->n_morph > GOFPID_MAX_MORPH_OPS) {
+        set_error("mat_morph has %d steps; at most %d are supported", cfg->n_morph, GOFPID_MAX_MORPH_OPS);
+        return GOFPID_ERR_UNSUPPORTED;
+    }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        set_error("no CUDA device available (libgofpid_b200 has no CPU fallback)");
+        return GOFPID_ERR_CUDA;
+    }
+    if (device < 0 || device >= ndev) {
+        set_error("device %d out of range [0, %d)", device, ndev);
+        return GOFPID_ERR_INVALID;
+    }
+    gofpid_pipeline *p = new (std::nothrow) gofpid_pipeline();
+    if (!p) { set_error("out of host memory"); return GOFPID_ERR_NOMEM; }
+    p->cfg = *cfg;
+    p->H = H; p->W = W; p->C = C; p->n_streams = n_streams; p->device = device;
+    // own the structuring elements
+    p->se_copies.resize(cfg->n_morph);
+    for (int i = 0; i < cfg->n_morph; i++) {
+        const gofpid_morph_op &o = cfg->morph[i];
+        if (o.kernel && o.kh > 0 && o.kw > 0) {
+            p->se_copies[i].assign(o.kernel, o.kernel + (size_t)o.kh * o.kw);
+            p->cfg.morph[i].kernel = p->se_copies[i].data();
+        }
+    }
+    DeviceGuard g(device);
+    int rc = g.ok ? build(p) : GOFPID_ERR_CUDA;
+    if (!g.ok) set_error("cannot select CUDA device %d", device);
+    if (rc != GOFPID_OK) {
+        free_all(p);
+        delete p;
+        cudaGetLastError();
+        return rc;
+    }
+    *out = p;
+    return GOFPID_OK;
+}
+
+GOFPID_API int gofpid_pipeline_destroy(gofpid_pipeline *p)
+{
+    if (!p) return GOFPID_OK;
+    {
+        DeviceGuard g(p->device);
+        cudaDeviceSynchronize();
+        free_all(p);
+    }
+    delete p;
+    return GOFPID_OK;
+}
+
+GOFPID_API int gofpid_pipeline_reset(gofpid_pipeline *p)
+{
+    GOFPID_GUARD(p);
+    GOFPID_CUDA_TRY(cudaDeviceSynchronize());
+    return reset_state(p);
+}
+
+GOFPID_API int gofpid_pipeline_process_device(gofpid_pipeline *p, const uint8_t *d_frames,
+                                              size_t pitch, size_t stream_stride, void *stream)
+{
+    GOFPID_GUARD(p);
+    if (!d_frames) { set_error("null frame pointer"); return GOFPID_ERR_INVALID; }
+    if (pitch < (size_t)p->W * p->C) { set_error("pitch %zu smaller than a row (%d bytes)", pitch, p->W * p->C); return GOFPID_ERR_INVALID; }
+    return run_step(p, d_frames, pitch, stream_stride, (cudaStream_t)stream);
+}
+
+GOFPID_API int gofpid_pipeline_process_host(gofpid_pipeline *p, const uint8_t *h_frames,
+                                            size_t pitch, size_t stream_stride)
+{
+    GOFPID_GUARD(p);
+    if (!h_frames) { set_error("null frame pointer"); return GOFPID_ERR_INVALID; }
+    const size_t row = (size_t)p->W * p->C;
+    if (pitch < row) { set_error("pitch %zu smaller than a row (%zu bytes)", pitch, row); return GOFPID_ERR_INVALID; }
+    if (!p->d_frames) {
+        p->frames_pitch = round_up(row, 128);
+        p->frames_stream = p->frames_pitch * p->H;
+        GOFPID_CUDA_TRY(cudaMalloc(&p->d_frames, p->frames_stream * p->n_streams));
+    }
+    cudaPointerAttributes attr;
+    bool pinned = false;
+    if (cudaPointerGetAttributes(&attr, h_frames) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
+    else cudaGetLastError();
+    const uint8_t *src = h_frames;
+    size_t spitch = pitch, sstride = stream_stride;
+    if (!pinned) {
+        if (!p->h_frames) GOFPID_CUDA_TRY(cudaMallocHost(&p->h_frames, row * p->H * p->n_streams));
+        for (int z = 0; z < p->n_streams; z++)
+            for (int y = 0; y < p->H; y++)
+                memcpy(p->h_frames + ((size_t)z * p->H + y) * row, h_frames + z * stream_stride + (size_t)y * pitch, row);
+        src = p->h_frames; spitch = row; sstride = row * p->H;
+    }
+    if (sstride == spitch * p->H || p->n_streams == 1) {
+        GOFPID_CUDA_TRY(cudaMemcpy2DAsync(p->d_frames, p->frames_pitch, src, spitch, row,
+                                          (size_t)p->H * p->n_streams, cudaMemcpyHostToDevice, p->stream));
+    } else {
+        for (int z = 0; z < p->n_streams; z++)
+            GOFPID_CUDA_TRY(cudaMemcpy2DAsync(p->d_frames + z * p->frames_stream, p->frames_pitch,
+                                              src + z * sstride, spitch, row, p->H,
+                                              cudaMemcpyHostToDevice, p->stream));
+    }
+    GOFPID_TRY(run_step(p, p->d_frames, p->frames_pitch, p->frames_stream, p->stream));
+    return fetch_results(p);
+}
+
+GOFPID_API int gofpid_pipeline_frame_info(gofpid_pipeline *p, int stream_idx, gofpid_frame_info *h_info)
+{
+    GOFPID_GUARD(p);
+    GOFPID_TRY(check_stream_index(p, stream_idx));
+    if (!h_info) { set_error("null output"); return GOFPID_ERR_INVALID; }
+    GOFPID_TRY(fetch_results(p));
+    *h_info = p->h_info[stream_idx];
+    return GOFPID_OK;
+}
+
+GOFPID_API int gofpid_pipeline_blobs(gofpid_pipeline *p, int stream_idx, gofpid_blob *h_blobs,
+                                     int blob_capacity, int32_t *h_points, int point_capacity,
+                                     int *n_blobs, int *n_points)
+{
+    GOFPID_GUARD(p);
+    GOFPID_TRY(check_stream_index(p, stream_idx));
+    if (!p->cfg.find_blobs) { set_error("pipeline was created with find_blobs = 0"); return GOFPID_ERR_INVALID; }
+    GOFPID_TRY(fetch_results(p));
+    const gofpid_frame_info &fi = p->h_info[stream_idx];
+    const int nk = std::min(fi.n_kept, p->blobs.max_kept);
+    const gofpid_blob *kb = p->h_kept + (size_t)stream_idx * p->blobs.max_kept;
+    const int32_t *pts = p->h_points + (size_t)stream_idx * p->blobs.max_points * 2;
+    // the reference's order: descending raster order of each component's first pixel
+    std::vector<int> order(nk);
+    for (int i = 0; i < nk; i++) order[i] = i;
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return kb[a].first > kb[b].first; });
+    int total = 0;
+    for (int i = 0; i < nk; i++) total += kb[order[i]].n_points;
+    if (n_blobs) *n_blobs = nk;
+    if (n_points) *n_points = total;
+    if (fi.overflow) {
+        set_error("blob capacity exceeded (flags %d): components %d/%d, kept %d/%d, points %d/%d",
+                  fi.overflow, fi.n_components, p->blobs.max_blobs, fi.n_kept, p->blobs.max_kept,
+                  fi.n_points, p->blobs.max_points);
+        return GOFPID_ERR_OVERFLOW;
+    }
+    if (!h_blobs && !h_points) return GOFPID_OK; // size query
+    if (nk > blob_capacity || total > point_capacity) {
+        set_error("output capacity too small: need %d blobs, %d points", nk, total);
+        return GOFPID_ERR_INVALID;
+    }
+    int off = 0;
+    for (int i = 0; i < nk; i++) {
+        gofpid_blob b = kb[order[i]];
+        if (h_points) memcpy(h_points + (size_t)off * 2, pts + (size_t)b.point_offset * 2, sizeof(int32_t) * 2 * b.n_points);
+        b.point_offset = off;
+        off += b.n_points;
+        if (h_blobs) h_blobs[i] = b;
+    }
+    return GOFPID_OK;
+}
+
+GOFPID_API int gofpid_pipeline_mask(gofpid_pipeline *p, int stream_idx, uint8_t *dst, size_t dst_pitch,
+                                    int dst_is_device)
+{
+    GOFPID_GUARD(p);
+    GOFPID_TRY(check_stream_index(p, stream_idx));
+    if (!dst || dst_pitch < (size_t)p->W) { set_error("bad destination"); return GOFPID_ERR_INVALID; }
+    if (!p->stepped) { set_error("no frame has been processed yet"); return GOFPID_ERR_INVALID; }
+    const uint8_t *src = p->d_mask[p->final_mask] + (size_t)stream_idx * p->mask_stream;
+    GOFPID_CUDA_TRY(cudaMemcpy2DAsync(dst, dst_pitch, src, p->mask_pitch, p->W, p->H,
+                                      dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
+                                      p->last_stream));
+    GOFPID_CUDA_TRY(cudaStreamSynchronize(p->last_stream));
+    return GOFPID_OK;
+}
+
+GOFPID_API int gofpid_pipeline_labels(gofpid_pipeline *p, int stream_idx, int32_t *dst, size_t dst_pitch,
+                                      int dst_is_device)
+{
+    GOFPID_GUARD(p);
+    GOFPID_TRY(check_stream_index(p, stream_idx));
+    if (!p->cfg.find_blobs) { set_error("pipeline was created with find_blobs = 0"); return GOFPID_ERR_INVALID; }
+    if (!dst || dst_pitch < (size_t)p->W * sizeof(int32_t) || dst_pitch % sizeof(int32_t)) { set_error("bad destination"); return GOFPID_ERR_INVALID; }
+    if (!p->stepped) { set_error("no frame has been processed yet"); return GOFPID_ERR_INVALID; }
+    cudaStream_t s = p->last_stream;
+    int32_t *tmp = nullptr;
+    int32_t *out = dst;
+    size_t out_pitch = dst_pitch / sizeof(int32_t);
+    if (!dst_is_device) {
+        GOFPID_CUDA_TRY(cudaMalloc(&tmp, (size_t)p->W * p->H * sizeof(int32_t)));
+        out = tmp; out_pitch = p->W;
+    }
+    int rc = launch_canonical_labels(p->d_mask[p->final_mask] + (size_t)stream_idx * p->mask_stream,
+                                     p->mask_pitch, p->blobs.labels + (size_t)stream_idx * p->blobs.labels_stream,
+                                     p->blobs.labels_pitch, out, out_pitch, p->H, p->W, s);
+    if (rc == GOFPID_OK && !dst_is_device) {
+        if (cudaMemcpy2DAsync(dst, dst_pitch, tmp, (size_t)p->W * sizeof(int32_t), (size_t)p->W * sizeof(int32_t),
+                              p->H, cudaMemcpyDeviceToHost, s) != cudaSuccess) { set_error("label copy failed"); rc = GOFPID_ERR_CUDA; }
+    }
+    if (cudaStreamSynchronize(s) != cudaSuccess && rc == GOFPID_OK) { set_error("label export failed: %s", cudaGetErrorString(cudaGetLastError())); rc = GOFPID_ERR_CUDA; }
+    if (tmp) cudaFree(tmp);
+    return rc;
+}
+
+GOFPID_API int gofpid_pipeline_components(gofpid_pipeline *p, int stream_idx, int32_t *h_stats, int capacity,
+                                          int *n_components)
+{
+    GOFPID_GUARD(p);
+    GOFPID_TRY(check_stream_index(p, stream_idx));
+    if (!p->cfg.find_blobs) { set_error("pipeline was created with find_blobs = 0"); return GOFPID_ERR_INVALID; }
+    GOFPID_TRY(fetch_results(p));
+    const gofpid_frame_info &fi = p->h_info[stream_idx];
+    const int n = std::min(fi.n_components, p->blobs.max_blobs);
+    if (n_components) *n_components = fi.n_components;
+    if (!h_stats) return GOFPID_OK;
+    if (n > capacity) { set_error("output capacity too small: need %d components", n); return GOFPID_ERR_INVALID; }
+    std::vector<int32_t> rec((size_t)n * 8);
+    if (n > 0)
+        GOFPID_CUDA_TRY(cudaMemcpy(rec.data(), p->blobs.comp + (size_t)stream_idx * p->blobs.max_blobs * 8,
+                                   rec.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
+    const int LP = (int)p->blobs.labels_pitch;
+    for (int i = 0; i < n; i++) {
+        const int32_t *r = &rec[(size_t)i * 8];
+        const int fy = r[0] / LP, fx = r[0] - fy * LP;
+        h_stats[i * 6 + 0] = fy * p->W + fx;
+        h_stats[i * 6 + 1] = r[1]; h_stats[i * 6 + 2] = r[2];
+        h_stats[i * 6 + 3] = r[3]; h_stats[i * 6 + 4] = r[4]; h_stats[i * 6 + 5] = r[5];
+    }
+    return GOFPID_OK;
+}
+
+GOFPID_API int gofpid_pipeline_mog2_model(gofpid_pipeline *p, int stream_idx, float *h_weight, float *h_var,
+                                          float *h_mean, uint8_t *h_nmodes)
+{
+    GOFPID_GUARD(p);
+    GOFPID_TRY(check_stream_index(p, stream_idx));
+    if (p->cfg.detector != GOFPID_DETECT_MOG2) { set_error("detector is not MOG2"); return GOFPID_ERR_INVALID; }
+    GOFPID_CUDA_TRY(cudaDeviceSynchronize());
+    const int H = p->H, W = p->W, C = p->C, PW = p->mog2.PW;
+    const size_t pe = p->mog2.plane_elems, np = p->mog2.stream_planes;
+    std::vector<float> planes(pe * np);
+    std::vector<uint8_t> nm(pe);
+    GOFPID_CUDA_TRY(cudaMemcpy(planes.data(), p->mog2.planes + (size_t)stream_idx * np * pe,
+                               planes.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    GOFPID_CUDA_TRY(cudaMemcpy(nm.data(), p->mog2.nmodes + (size_t)stream_idx * pe, pe, cudaMemcpyDeviceToHost));
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            const size_t s = (size_t)y * PW + x, d = (size_t)y * W + x;
+            if (h_nmodes) h_nmodes[d] = nm[s];
+            for (int k = 0; k < 5; k++) {
+                if (h_weight) h_weight[d * 5 + k] = planes[(size_t)k * pe + s];
+                if (h_var) h_var[d * 5 + k] = planes[(size_t)(5 + k) * pe + s];
+                if (h_mean)
+                    for (int c = 0; c < C; c++) h_mean[(d * 5 + k) * C + c] = planes[(size_t)(10 + k * C + c) * pe + s];
+            }
+        }
+    return GOFPID_OK;
+}
+
+GOFPID_API int gofpid_pipeline_knn_model(gofpid_pipeline *p, int stream_idx, uint8_t *h_samples, uint8_t *h_idx,
+                                         uint8_t *h_nxt, int32_t *h_counters, uint64_t *rng_state)
+{
+    GOFPID_GUARD(p);
+    GOFPID_TRY(check_stream_index(p, stream_idx));
+    if (p->cfg.detector != GOFPID_DETECT_KNN) { set_error("detector is not KNN"); return GOFPID_ERR_INVALID; }
+    GOFPID_CUDA_TRY(cudaDeviceSynchronize());
+    const int H = p->H, W = p->W, ND = p->C + 1, PW = p->knn.PW;
+    const size_t pe = p->knn.plane_elems, n = (size_t)H * W;
+    std::vector<uint8_t> smp(pe * 21 * ND);
+    std::vector<uint32_t> nxt(pe);
+    std::vector<uint16_t> idx(pe);
+    FrameTick t;
+    GOFPID_CUDA_TRY(cudaMemcpy(smp.data(), p->knn.samples + (size_t)stream_idx * smp.size(), smp.size(), cudaMemcpyDeviceToHost));
+    GOFPID_CUDA_TRY(cudaMemcpy(nxt.data(), p->knn.nxt + (size_t)stream_idx * pe, pe * 4, cudaMemcpyDeviceToHost));
+    GOFPID_CUDA_TRY(cudaMemcpy(idx.data(), p->knn.idx + (size_t)stream_idx * pe, pe * 2, cudaMemcpyDeviceToHost));
+    GOFPID_CUDA_TRY(cudaMemcpy(&t, p->d_tick, sizeof(t), cudaMemcpyDeviceToHost));
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            const size_t s = (size_t)y * PW + x, d = (size_t)y * W + x;
+            if (h_samples)
+                for (int k = 0; k < 21; k++)
+                    for (int c = 0; c < ND; c++) h_samples[(d * 21 + k) * ND + c] = smp[((size_t)k * pe + s) * ND + c];
+            if (h_idx) { h_idx[d] = idx[s] & 7; h_idx[n + d] = (idx[s] >> 3) & 7; h_idx[2 * n + d] = (idx[s] >> 6) & 7; }
+            if (h_nxt) { h_nxt[d] = nxt[s] & 255; h_nxt[n + d] = (nxt[s] >> 8) & 255; h_nxt[2 * n + d] = (nxt[s] >> 16) & 255; }
+        }
+    if (h_counters) {
+        // counters as OpenCV holds them AFTER the last frame
+        for (int k = 0; k < 3; k++) {
+            int c = t.knn_counter[k];
+            if (t.nframes > 0) { c++; if (c >= t.knn_u[k]) c = 0; }
+            h_counters[k] = c;
+        }
+    }
+    if (rng_state) *rng_state = t.knn_rng;
+    return GOFPID_OK;
+}
+
+GOFPID_API int gofpid_pipeline_fd_model(gofpid_pipeline *p, int stream_idx, uint8_t *h_prev, int *valid)
+{
+    GOFPID_GUARD(p);
+    GOFPID_TRY(check_stream_index(p, stream_idx));
+    if (p->cfg.detector != GOFPID_DETECT_FD) { set_error("detector is not FD"); return GOFPID_ERR_INVALID; }
+    GOFPID_CUDA_TRY(cudaDeviceSynchronize());
+    FrameTick t;
+    GOFPID_CUDA_TRY(cudaMemcpy(&t, p->d_tick, sizeof(t), cudaMemcpyDeviceToHost));
+    if (valid) *valid = t.nframes > 0;
+    if (h_prev)
+        GOFPID_CUDA_TRY(cudaMemcpy2D(h_prev, (size_t)p->W * p->C, p->fd.prev + (size_t)stream_idx * p->fd.stream_stride,
+                                     p->fd.pitch, (size_t)p->W * p->C, p->H, cudaMemcpyDeviceToHost));
+    return GOFPID_OK;
+}
+
+GOFPID_API int gofpid_pipeline_mog2_mean_modes(gofpid_pipeline *p, double *mean_modes)
+{
+    GOFPID_GUARD(p);
+    if (p->cfg.detector != GOFPID_DETECT_MOG2) { set_error("detector is not MOG2"); return GOFPID_ERR_INVALID; }
+    if (!mean_modes) { set_error("null output"); return GOFPID_ERR_INVALID; }
+    GOFPID_CUDA_TRY(cudaDeviceSynchronize());
+    const size_t pe = p->mog2.plane_elems;
+    std::vector<uint8_t> nm(pe * p->n_streams);
+    GOFPID_CUDA_TRY(cudaMemcpy(nm.data(), p->mog2.nmodes, nm.size(), cudaMemcpyDeviceToHost));
+    double sum = 0;
+    for (int z = 0; z < p->n_streams; z++)
+        for (int y = 0; y < p->H; y++)
+            for (int x = 0; x < p->W; x++) sum += nm[(size_t)z * pe + (size_t)y * p->mog2.PW + x];
+    *mean_modes = sum / ((double)p->n_streams * p->H * p->W);
+    return GOFPID_OK;
+}
+
+GOFPID_API int gofpid_pipeline_set_profiling(gofpid_pipeline *p, int enabled)
+{
+    GOFPID_GUARD(p);
+    p->profiling = enabled != 0;
+    return GOFPID_OK;
+}
+
+GOFPID_API int gofpid_pipeline_stage_ms(gofpid_pipeline *p, float *h_ms5)
+{
+    GOFPID_GUARD(p);
+    if (!h_ms5) { set_error("null output"); return GOFPID_ERR_INVALID; }
+    if (!p->profiling || !p->stepped) { set_error("profiling is off or no frame processed"); return GOFPID_ERR_INVALID; }
+    GOFPID_CUDA_TRY(cudaEventSynchronize(p->ev[3]));
+    float blobs_ms = 0.f;
+    GOFPID_CUDA_TRY(cudaEventElapsedTime(&h_ms5[0], p->ev[0], p->ev[1]));
+    GOFPID_CUDA_TRY(cudaEventElapsedTime(&h_ms5[1], p->ev[1], p->ev[2]));
+    GOFPID_CUDA_TRY(cudaEventElapsedTime(&blobs_ms, p->ev[2], p->ev[3]));
+    h_ms5[2] = blobs_ms; h_ms5[3] = 0.f;
+    GOFPID_CUDA_TRY(cudaEventElapsedTime(&h_ms5[4], p->ev[0], p->ev[3]));
+    return GOFPID_OK;
+}
+
+GOFPID_API int gofpid_pipeline_launch_count(gofpid_pipeline *p)
+{
+    return p ? p->launch_count : 0;
+}
+
+// =====================================================================================
+// stage-level entry points
+// =====================================================================================
+GOFPID_API int gofpid_blur_u8(const uint8_t *d_src, size_t src_pitch, uint8_t *d_dst, size_t dst_pitch,
+                              int H, int W, int C, int kind, int kw, int kh, double sigma, void *stream)
+{
+    if (!d_src || !d_dst || H <= 0 || W <= 0) { set_error("bad argument"); return GOFPID_ERR_INVALID; }
+    if (gofpid_device_count() == 0) { set_error("no CUDA device available (no CPU fallback)"); return GOFPID_ERR_CUDA; }
+    DetectLaunch L;
+    L.H = H; L.W = W; L.C = C; L.n_streams = 1;
+    L.src = FrameSrc{d_src, src_pitch, 0};
+    GOFPID_TRY(make_blur_params(kind, kw, kh, sigma, &L.blur));
+    L.mask = ImageU8{nullptr, 0, 0};
+    L.tick = nullptr;
+    L.stream = (cudaStream_t)stream;
+    return launch_blur_only(L, ImageU8{d_dst, dst_pitch, 0});
+}
+
+GOFPID_API int gofpid_morph_u8(const uint8_t *d_src, size_t src_pitch, uint8_t *d_dst, size_t dst_pitch,
+                               int H, int W, const gofpid_morph_op *ops, int n_ops, void *stream)
+{
+    if (!d_src || !d_dst || H <= 0 || W <= 0 || (n_ops > 0 && !ops)) { set_error("bad argument"); return GOFPID_ERR_INVALID; }
+    if (gofpid_device_count() == 0) { set_error("no CUDA device available (no CPU fallback)"); return GOFPID_ERR_CUDA; }
+    MorphPlan plan;
+    GOFPID_TRY(morph_plan_create(ops, n_ops, &plan));
+    int rc = launch_morph(plan, ImageU8{const_cast<uint8_t *>(d_src), src_pitch, 0}, ImageU8{d_dst, dst_pitch, 0},
+                          H, W, 1, (cudaStream_t)stream);
+    if (rc == GOFPID_OK && cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) {
+        set_error("morphology kernel failed: %s", cudaGetErrorString(cudaGetLastError()));
+        rc = GOFPID_ERR_CUDA;
+    }
+    morph_plan_destroy(&plan);
+    return rc;
+}
+
+GOFPID_API int gofpid_ccl_u8(const uint8_t *d_mask, size_t mask_pitch, int32_t *d_labels, size_t labels_pitch,
+                             int H, int W, void *stream)
+{
+    if (!d_mask || !d_labels || H <= 0 || W <= 0 || labels_pitch % sizeof(int32_t)) { set_error("bad argument"); return GOFPID_ERR_INVALID; }
+    if (gofpid_device_count() == 0) { set_error("no CUDA device available (no CPU fallback)"); return GOFPID_ERR_CUDA; }
+    return launch_ccl_only(d_mask, mask_pitch, d_labels, labels_pitch / sizeof(int32_t), H, W, (cudaStream_t)stream);
+}
+
+} // extern "C"

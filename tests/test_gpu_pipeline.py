@@ -1,0 +1,244 @@
+"""GPU parity of the pipeline handle (through the C ABI) against the CPU oracle.
+
+FD / MOG2 / KNN masks and model state are compared bit-for-bit with oracle/gofpid_oracle.c
+(itself pinned to cv2 4.13 and to the reference-generated vectors in tests/golden/), far
+inside the <= 0.1 % mask-disagreement bar BASELINE.json allows for the mixture models.
+Blob lists (contours, order, centre / bottom) are compared with the oracle's restatement of
+cv.findContours(RETR_EXTERNAL, CHAIN_APPROX_NONE) + contourArea + moments.
+"""
+import numpy as np
+import pytest
+
+from oracle import blobs as oblobs
+from oracle import cport
+from pygofpid_b200.synth import SyntheticClip
+
+pytestmark = pytest.mark.gpu
+
+
+def _hot(*a, **k):
+    from pygofpid_b200 import HotPath
+    return HotPath(*a, **k)
+
+
+def _shape(H, W, C):
+    return (H, W) if C == 1 else (H, W, C)
+
+
+# ----------------------------------------------------------------------------- FD
+@pytest.mark.parametrize("H,W,C", [(64, 50, 1), (20, 32, 3), (240, 320, 1), (33, 131, 3)])
+@pytest.mark.parametrize("blur", [None, ("gaussian", (3, 3), 4.0), ("box", (3, 3))])
+def test_fd_masks_and_state(H, W, C, blur):
+    hp = _hot(_shape(H, W, C), blur=blur, detector="FD", morph=(), find_blobs=False, fd_threshold=7.5)
+    fd = cport.FrameDifferencing(7.5)
+    clip = SyntheticClip(H, W, C, seed=3, n_obj=3)
+    for t in range(6):
+        f = clip.next()
+        b = f
+        if blur and blur[0] == "gaussian":
+            b = cport.gaussian_blur(f, blur[1], blur[2]).reshape(f.shape)
+        elif blur:
+            b = cport.box_blur(f, blur[1]).reshape(f.shape)
+        want = fd.apply(b)
+        hp.process(f)
+        got = hp.mask()
+        assert got.shape == (H, W)
+        assert np.array_equal(got, want), (t, int((got != want).sum()))
+        assert np.array_equal(hp.fd_model(), b)
+    if C == 3:
+        assert set(np.unique(got)) <= {0, 84, 85}
+
+
+# ----------------------------------------------------------------------------- MOG2
+@pytest.mark.parametrize("H,W,C,sigma", [(48, 64, 1, 6), (48, 64, 3, 6), (37, 53, 1, 25), (37, 53, 3, 25),
+                                          (120, 200, 1, 4)])
+def test_mog2_masks_and_model_bitexact(H, W, C, sigma):
+    hp = _hot(_shape(H, W, C), blur=None, detector="MOG2", morph=(), find_blobs=False)
+    ora = cport.MOG2(H, W, C)
+    clip = SyntheticClip(H, W, C, seed=10 * C + sigma, n_obj=4, noise_sigma=sigma)
+    nframes = 300 if H * W < 5000 else 120
+    for t in range(nframes):
+        f = clip.next()
+        want = ora.apply(f)
+        hp.process(f)
+        got = hp.mask()
+        assert np.array_equal(got, want), (t, int((got != want).sum()))
+        if t in (0, 1, 7, nframes - 1):
+            w, v, m, k = hp.mog2_model()
+            ow, ov, om, ok = ora.planes()
+            assert np.array_equal(k, ok), t
+            live = np.arange(5)[None, None, :] < ok[..., None]
+            assert np.array_equal(w[live], ow[live]), t
+            assert np.array_equal(v[live], ov[live]), t
+            assert np.array_equal(m[live], om[live]), t
+    assert set(np.unique(got)) <= {0, 127, 255}
+    assert abs(hp.mog2_mean_modes() - ok.mean()) < 1e-9
+
+
+def test_mog2_first_frame_is_shadow_everywhere():
+    hp = _hot((32, 40), blur=None, detector="MOG2", find_blobs=False)
+    f = np.full((32, 40), 90, np.uint8)
+    f[3, 4] = 0
+    hp.process(f)
+    m = hp.mask()
+    assert m[3, 4] == 255 and (np.delete(m.ravel(), 3 * 40 + 4) == 127).all()
+    hp.process(f)
+    assert (hp.mask() == 0).all()
+    hp.reset()
+    hp.process(f)
+    assert np.array_equal(hp.mask(), m)
+
+
+# ----------------------------------------------------------------------------- KNN
+@pytest.mark.parametrize("H,W,C", [(37, 53, 1), (37, 53, 3), (50, 66, 1), (64, 128, 1)])
+def test_knn_masks_and_state_bitexact(H, W, C):
+    seed = 12345
+    hp = _hot(_shape(H, W, C), blur=None, detector="KNN", morph=(), find_blobs=False, knn_seed=seed)
+    ora = cport.KNN(H, W, C, seed)
+    clip = SyntheticClip(H, W, C, seed=C, n_obj=4)
+    for t in range(200):
+        f = clip.next()
+        want = ora.apply(f)
+        hp.process(f)
+        got = hp.mask()
+        assert np.array_equal(got, want), (t, int((got != want).sum()))
+        if t in (0, 5, 60, 199):
+            s, idx, nxt, cnt, rng = hp.knn_model()
+            os_, oidx, onxt, ocnt, orng = ora.state()
+            assert np.array_equal(s, os_), t
+            assert np.array_equal(idx, oidx), t
+            assert np.array_equal(nxt, onxt), t
+            assert list(cnt) == list(ocnt), t
+            assert rng == orng, t
+
+
+# ----------------------------------------------------------------------------- fused chain
+@pytest.mark.parametrize("det,C", [("MOG2", 1), ("MOG2", 3), ("KNN", 1), ("FD", 1)])
+def test_fused_blur_detect_morph(det, C):
+    H, W = 90, 150
+    r5 = np.ones((5, 5), np.uint8)
+    morph = [("erode", r5), ("dilate", r5)]
+    hp = _hot(_shape(H, W, C), blur=("gaussian", (3, 3), 4.0), detector=det, morph=morph,
+              find_blobs=False, knn_seed=99)
+    ora = {"MOG2": lambda: cport.MOG2(H, W, C), "KNN": lambda: cport.KNN(H, W, C, 99),
+           "FD": lambda: cport.FrameDifferencing(5)}[det]()
+    clip = SyntheticClip(H, W, C, seed=21, n_obj=5)
+    for t in range(40):
+        f = clip.next()
+        b = cport.gaussian_blur(f, (3, 3), 4.0).reshape(f.shape)
+        want = cport.dilate(cport.erode(ora.apply(b), r5), r5)
+        hp.process(f)
+        got = hp.mask()
+        assert np.array_equal(got, want), (det, t, int((got != want).sum()))
+
+
+# ----------------------------------------------------------------------------- blobs
+def _blob_masks():
+    import cv2
+    rs = np.random.RandomState(5)
+    out = []
+    for it in range(24):
+        H, W = rs.randint(20, 140), rs.randint(20, 300)
+        if it % 4 == 0:
+            M = ((rs.rand(H, W) < 0.5) * 255).astype(np.uint8)
+        else:
+            M = np.zeros((H, W), np.uint8)
+            for _ in range(10):
+                x, y = rs.randint(0, W), rs.randint(0, H)
+                w, h = rs.randint(2, 60), rs.randint(2, 60)
+                cv2.rectangle(M, (x, y), (x + w, y + h), int(rs.choice([127, 255])),
+                              int(rs.choice([-1, 1, 2])))
+            M[rs.rand(H, W) < 0.03] = 0
+        out.append(M)
+    # nested rings: only the outermost component is external
+    M = np.zeros((60, 60), np.uint8)
+    cv2.rectangle(M, (2, 2), (57, 57), 255, 2)
+    cv2.rectangle(M, (10, 10), (49, 49), 255, 2)
+    cv2.rectangle(M, (20, 20), (39, 39), 255, -1)
+    out.append(M)
+    out.append(np.full((40, 70), 255, np.uint8))
+    out.append(np.zeros((40, 70), np.uint8))
+    return out
+
+
+def test_blobs_match_reference_semantics():
+    """Feed masks through FD (|mask - 0| > 0 keeps them as they are) and compare the blob list."""
+    for M in _blob_masks():
+        H, W = M.shape
+        for area_min in (100.0, 0.0):
+            hp = _hot((H, W), blur=None, detector="FD", morph=(), find_blobs=True, fd_threshold=0,
+                      area_min=area_min)
+            hp.process(np.zeros((H, W), np.uint8))
+            hp.process(M)
+            got_mask = hp.mask()
+            want_mask = np.where(M > 0, 255, 0).astype(np.uint8)
+            assert np.array_equal(got_mask, want_mask)
+            # labels and per-component statistics
+            want_labels = cport.ccl8(want_mask)
+            assert np.array_equal(hp.labels(), want_labels)
+            assert hp.components() == cport.component_stats(want_labels)
+            want = oblobs.blobs_from_mask(want_mask, area_min=area_min)
+            got = hp.blobs()
+            assert len(got) == len(want), (M.shape, area_min, len(got), len(want))
+            for g, w in zip(got, want):
+                assert g["contour"].dtype == np.int32 and g["contour"].shape == w["contour"].shape
+                assert np.array_equal(g["contour"], w["contour"])
+                assert np.array_equal(g["bottom"], w["bottom"]) and g["bottom"].dtype == np.int16
+                assert np.array_equal(g["center"], w["center"])
+                assert np.array_equal(g["anchor"], w["anchor"])
+            hp.close()
+
+
+def test_blob_capacity_overflow_is_reported():
+    from pygofpid_b200._native import GofpidError
+    H, W = 64, 64
+    M = np.zeros((H, W), np.uint8)
+    M[::2, ::2] = 255  # 1024 isolated pixels
+    hp = _hot((H, W), blur=None, detector="FD", find_blobs=True, fd_threshold=0, max_blobs=100)
+    hp.process(np.zeros((H, W), np.uint8))
+    hp.process(M)
+    assert hp.frame_info()["overflow"] & 1
+    with pytest.raises(GofpidError):
+        hp.blobs()
+
+
+# ----------------------------------------------------------------------------- streams
+def test_streams_are_independent_and_match_single_stream_runs():
+    H, W, S = 48, 80, 3
+    r3 = np.ones((3, 3), np.uint8)
+    morph = [("erode", r3), ("dilate", r3)]
+    multi = _hot((H, W), detector="MOG2", morph=morph, n_streams=S, area_min=20)
+    singles = [_hot((H, W), detector="MOG2", morph=morph, n_streams=1, area_min=20) for _ in range(S)]
+    clips = [SyntheticClip(H, W, 1, seed=100 + i, n_obj=3) for i in range(S)]
+    for t in range(25):
+        frames = np.stack([c.next() for c in clips])
+        multi.process(frames)
+        for i in range(S):
+            singles[i].process(frames[i])
+            assert np.array_equal(multi.mask(i), singles[i].mask())
+            a, b = multi.blobs(i), singles[i].blobs()
+            assert len(a) == len(b)
+            for x, y in zip(a, b):
+                assert np.array_equal(x["contour"], y["contour"])
+
+
+def test_device_resident_frames_match_host_frames():
+    import torch
+    H, W = 60, 100
+    a = _hot((H, W), detector="MOG2", find_blobs=True, area_min=10)
+    b = _hot((H, W), detector="MOG2", find_blobs=True, area_min=10)
+    clip = SyntheticClip(H, W, 1, seed=8)
+    for t in range(10):
+        f = clip.next()
+        a.process(f)
+        d = torch.from_numpy(f).cuda()
+        b.process_device(d.data_ptr(), W, W * H, torch.cuda.current_stream().cuda_stream)
+        assert np.array_equal(a.mask(), b.mask())
+        assert a.frame_info() == b.frame_info()
+
+
+def test_shape_change_raises_value_error():
+    hp = _hot((20, 30), detector="FD", find_blobs=False)
+    hp.process(np.zeros((20, 30), np.uint8))
+    with pytest.raises(ValueError):
+        hp.process(np.zeros((21, 30), np.uint8))
