@@ -201,7 +201,8 @@ GOFPID_API int gofpid_pipeline_mog2_mean_modes(gofpid_pipeline *p, double *mean_
 
 /* Timing aid for bench.py: device time (ms, CUDA events on the pipeline's launch stream)
  * spent in each stage kernel group during the last process call:
- * [0] blur+detect, [1] morphology, [2] labelling+stats, [3] contours, [4] whole step. */
+ * [0] fused blur+detect kernel(s), [1] morphology, [2] labelling+stats+contours,
+ * [3] frame tick, [4] whole step. */
 GOFPID_API int gofpid_pipeline_set_profiling(gofpid_pipeline *p, int enabled);
 GOFPID_API int gofpid_pipeline_stage_ms(gofpid_pipeline *p, float *h_ms5);
 /* Number of kernels the last process call launched. */

@@ -268,6 +268,7 @@ int run_step(gofpid_pipeline *p, const uint8_t *d_frames, size_t pitch, size_t s
     if (prof) GOFPID_CUDA_TRY(cudaEventRecord(p->ev[0], s));
     GOFPID_TRY(launch_tick(p->d_tick, p->cfg.detector, p->mog2p, p->knnp, p->d_knn_table,
                            p->knn_table_len, p->d_pow2tab, p->H, p->W, p->n_streams, s));
+    if (prof) GOFPID_CUDA_TRY(cudaEventRecord(p->ev[4], s));
     DetectLaunch L;
     L.H = p->H; L.W = p->W; L.C = p->C; L.n_streams = p->n_streams;
     L.src = FrameSrc{d_frames, pitch, stream_stride};
@@ -750,10 +751,11 @@ GOFPID_API int gofpid_pipeline_stage_ms(gofpid_pipeline *p, float *h_ms5)
     if (!p->profiling || !p->stepped) { set_error("profiling is off or no frame processed"); return GOFPID_ERR_INVALID; }
     GOFPID_CUDA_TRY(cudaEventSynchronize(p->ev[3]));
     float blobs_ms = 0.f;
-    GOFPID_CUDA_TRY(cudaEventElapsedTime(&h_ms5[0], p->ev[0], p->ev[1]));
+    GOFPID_CUDA_TRY(cudaEventElapsedTime(&h_ms5[0], p->ev[4], p->ev[1]));
     GOFPID_CUDA_TRY(cudaEventElapsedTime(&h_ms5[1], p->ev[1], p->ev[2]));
     GOFPID_CUDA_TRY(cudaEventElapsedTime(&blobs_ms, p->ev[2], p->ev[3]));
-    h_ms5[2] = blobs_ms; h_ms5[3] = 0.f;
+    h_ms5[2] = blobs_ms;
+    GOFPID_CUDA_TRY(cudaEventElapsedTime(&h_ms5[3], p->ev[0], p->ev[4]));
     GOFPID_CUDA_TRY(cudaEventElapsedTime(&h_ms5[4], p->ev[0], p->ev[3]));
     return GOFPID_OK;
 }

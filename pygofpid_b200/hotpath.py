@@ -264,7 +264,7 @@ class HotPath:
     def stage_ms(self):
         ms = (ct.c_float * 5)()
         nat.check(self._L.gofpid_pipeline_stage_ms(self._h, ms))
-        return dict(detect=ms[0], morph=ms[1], blobs=ms[2], step=ms[4])
+        return dict(detect=ms[0], morph=ms[1], blobs=ms[2], tick=ms[3], step=ms[4])
 
     def launch_count(self):
         return int(self._L.gofpid_pipeline_launch_count(self._h))

@@ -165,7 +165,7 @@ def test_blobs_match_reference_semantics():
     """Feed masks through FD (|mask - 0| > 0 keeps them as they are) and compare the blob list."""
     for M in _blob_masks():
         H, W = M.shape
-        for area_min in (100.0, 0.0):
+        for area_min in (100.0, 0.5):
             hp = _hot((H, W), blur=None, detector="FD", morph=(), find_blobs=True, fd_threshold=0,
                       area_min=area_min)
             hp.process(np.zeros((H, W), np.uint8))
