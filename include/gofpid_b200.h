@@ -127,7 +127,7 @@ typedef struct gofpid_frame_info {
     int32_t n_candidates; /* external components passing the bbox pre-filter           */
     int32_t n_kept;       /* blobs in the output list                                  */
     int32_t n_points;     /* contour points in the pool                                */
-    int32_t overflow;     /* bit0: components, bit1: kept blobs, bit2: points          */
+    int32_t overflow;     /* bit0: components, bit1: kept blobs, bit2: points, bit3: internal */
     int32_t frame_index;  /* 1-based count of frames this stream has processed         */
     int32_t reserved[2];
 } gofpid_frame_info;

@@ -26,12 +26,16 @@
 
 namespace gofpid {
 
-constexpr int CCL_TW = 128;
-constexpr int CCL_TH = 16;
-constexpr int CCL_THREADS = 32 * CCL_TH; // each thread owns 4 consecutive pixels of a row
+constexpr int CCL_TW = 64;  // one 64-bit word of class bits per tile row
+constexpr int CCL_TH = 32;
+constexpr int CCL_THREADS = 16 * CCL_TH; // each thread owns 4 consecutive pixels of a row
 
-constexpr int TRACE_THREADS = 128;
-constexpr int TRACE_SMEM_WORDS = 40 * 1024; // 160 KB bitmap: boxes up to ~1.3 Mpx
+constexpr int TRACE_THREADS = 256;
+constexpr int TRACE_SMEM_WORDS = 32 * 1024; // 128 KB bitmap: boxes up to ~1 Mpx
+constexpr int TRACE_MAX_CP = 1024;          // checkpoints per contour
+constexpr int TRACE_HT = 2048;              // hash slots (power of two, >= 2 * TRACE_MAX_CP)
+constexpr size_t TRACE_SMEM_BYTES = (size_t)TRACE_SMEM_WORDS * 4 + (size_t)TRACE_MAX_CP * (32 + 8) +
+                                    (size_t)TRACE_HT * 8;
 
 // component record layout (8 int32)
 enum { CR_FIRST = 0, CR_X0, CR_Y0, CR_X1, CR_Y1, CR_AREA, CR_PAD0, CR_PAD1, CR_SIZE };
@@ -82,15 +86,36 @@ __device__ __forceinline__ void uf_union_g(int32_t *lab, int a, int b)
 }
 
 // ------------------------------------------------------------------------------------
-// 1. tile-local labelling
+// 1. tile-local labelling (run based)
 // ------------------------------------------------------------------------------------
+// Every tile row is one 64-bit word of foreground bits.  A pixel's provisional label is the
+// start of its horizontal run (found with clz on the row word), so no horizontal unions are
+// needed; only the thread that owns a run start joins the run with the runs it touches in the
+// row above (8-connected for foreground, 4-connected for background).
+__device__ __forceinline__ unsigned long long bits_below(int x) // bits [0, x)
+{
+    return x >= 64 ? ~0ULL : ((1ULL << x) - 1ULL);
+}
+// start / end of the maximal run of set bits of `S` that contains bit x
+__device__ __forceinline__ int run_start(unsigned long long S, int x)
+{
+    const unsigned long long brk = ~S & bits_below(x);
+    return brk ? 64 - __clzll((long long)brk) : 0;
+}
+__device__ __forceinline__ int run_end(unsigned long long S, int x)
+{
+    const unsigned long long brk = ~S & ~bits_below(x + 1);
+    return brk ? __ffsll((long long)brk) - 2 : 63;
+}
+
 __global__ void __launch_bounds__(CCL_THREADS)
 label_tiles_kernel(ImageU8 mask, int32_t *labels, size_t LP, size_t labels_stream, int H, int W,
                    gofpid_frame_info *info, const FrameTick *tick)
 {
     __shared__ int lab[CCL_TW * CCL_TH];
-    __shared__ uint8_t cls[(CCL_TH + 1) * (CCL_TW + 2)]; // row -1 and columns -1, TW unused/none
-    const int tx = threadIdx.x, ty = threadIdx.y;
+    __shared__ unsigned int Fw[CCL_TH][2]; // foreground bits of each tile row (two 32-bit halves)
+    const int tx = threadIdx.x, ty = threadIdx.y; // blockDim = (16, CCL_TH)
+    const int lane = (ty * 16 + tx) & 31;
     const int x0 = blockIdx.x * CCL_TW, y0 = blockIdx.y * CCL_TH;
     const int lx = tx * 4, x = x0 + lx, y = y0 + ty;
     const uint8_t *mrow = mask.base + (size_t)blockIdx.z * mask.stream_stride + (size_t)y * mask.pitch;
@@ -101,38 +126,64 @@ label_tiles_kernel(ImageU8 mask, int32_t *labels, size_t LP, size_t labels_strea
         fi->overflow = 0; fi->frame_index = tick ? tick->nframes : 0;
     }
 
-    // class per pixel: 0 background, 1 foreground, 2 outside the image
     uint32_t mw = 0;
     if (y < H && x < W) mw = *reinterpret_cast<const uint32_t *>(mrow + x); // padded pitch
-    int c[4];
+    unsigned nib = 0;
 #pragma unroll
-    for (int j = 0; j < 4; j++) {
-        c[j] = (y < H && x + j < W) ? (((mw >> (8 * j)) & 255) != 0 ? 1 : 0) : 2;
-        const int li = ty * CCL_TW + lx + j;
-        const bool frame_edge = y == 0 || y == H - 1 || x + j == 0 || x + j == W - 1;
-        lab[li] = (c[j] == 0 && frame_edge) ? 0 : li + 1;
-        cls[(ty + 1) * (CCL_TW + 2) + lx + j + 1] = (uint8_t)c[j];
-    }
-    if (ty == 0) {
-#pragma unroll
-        for (int j = 0; j < 4; j++) cls[lx + j + 1] = 2;
-        if (tx == 0) { cls[0] = 2; cls[CCL_TW + 1] = 2; }
-    }
-    if (tx == 0) { cls[(ty + 1) * (CCL_TW + 2)] = 2; cls[(ty + 1) * (CCL_TW + 2) + CCL_TW + 1] = 2; }
+    for (int j = 0; j < 4; j++)
+        if (y < H && x + j < W && ((mw >> (8 * j)) & 255) != 0) nib |= 1u << j;
+    // the 8 lanes that share a 32-pixel half row OR their nibbles together
+    const unsigned grp = 0xffu << (lane & 24);
+    const unsigned half = __reduce_or_sync(grp, nib << (4 * (tx & 7)));
+    if ((tx & 7) == 0) Fw[ty][tx >> 3] = half;
     __syncthreads();
 
+    const int wvalid = min(CCL_TW, W - x0);                 // valid columns of this tile
+    const unsigned long long V = bits_below(wvalid);
+    const bool row_ok = y < H;
+    const unsigned long long F = ((unsigned long long)Fw[ty][1] << 32) | Fw[ty][0];
+    unsigned long long Fp = 0, Vp = 0;
+    if (ty > 0) { Fp = ((unsigned long long)Fw[ty - 1][1] << 32) | Fw[ty - 1][0]; Vp = V; }
+
+    // provisional labels: every pixel points at its run start; a background run that touches
+    // the frame border is the virtual OUTSIDE node (0)
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        if (c[j] == 2) continue;
-        const int li = ty * CCL_TW + lx + j;
-        const uint8_t *cr = cls + (ty + 1) * (CCL_TW + 2) + lx + j + 1;
-        const int cw = cr[-1], cn = cr[-(CCL_TW + 2)], cnw = cr[-(CCL_TW + 2) - 1],
-                  cne = cr[-(CCL_TW + 2) + 1];
-        if (cw == c[j]) uf_union_s(lab, li + 1, li);
-        if (cn == c[j]) uf_union_s(lab, li + 1, li + 1 - CCL_TW);
-        if (c[j] == 1 && cn != 1) {
-            if (cnw == 1 && cw != 1) uf_union_s(lab, li + 1, li - CCL_TW);
-            if (cne == 1) uf_union_s(lab, li + 1, li + 2 - CCL_TW);
+        const int c = lx + j;
+        const int li = ty * CCL_TW + c;
+        if (!row_ok || c >= wvalid) { lab[li] = li + 1; continue; }
+        const bool fg = (F >> c) & 1ULL;
+        const unsigned long long S = fg ? F : (~F & V);
+        const int a = run_start(S, c);
+        int v = ty * CCL_TW + a + 1;
+        if (a == c && !fg) {
+            const int b = run_end(S, c);
+            if (y == 0 || y == H - 1 || x0 + a == 0 || x0 + b == W - 1) v = 0;
+        }
+        lab[li] = v;
+    }
+    __syncthreads();
+
+    // vertical unions, one thread per run
+    if (row_ok && ty > 0) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int c = lx + j;
+            if (c >= wvalid) continue;
+            const bool fg = (F >> c) & 1ULL;
+            const unsigned long long S = fg ? F : (~F & V);
+            if (run_start(S, c) != c) continue;
+            const int b = run_end(S, c);
+            const unsigned long long Sp = fg ? Fp : (~Fp & Vp);
+            const int lo = fg ? max(c - 1, 0) : c, hi = fg ? min(b + 1, 63) : b;
+            unsigned long long m = Sp & bits_below(hi + 1) & ~bits_below(lo);
+            const int me = ty * CCL_TW + c + 1;
+            while (m) {
+                const int pos = __ffsll((long long)m) - 1;
+                const int ap = run_start(Sp, pos), bp = run_end(Sp, pos);
+                uf_union_s(lab, me, (ty - 1) * CCL_TW + ap + 1);
+                m &= ~bits_below(bp + 1);
+            }
         }
     }
     __syncthreads();
@@ -283,6 +334,7 @@ struct BitmapView { // component staged in smem with a 1-pixel empty frame
     const uint32_t *bits;
     int row_words;
     int bx0, by0; // image coords of bitmap (1, 1)
+    int sx, sy;   // the component's first pixel (start of the border)
     __device__ __forceinline__ unsigned nb(int x, int y) const
     {
         const int bx = x - bx0, by = y - by0; // bitmap column of x-1 is bx, row of y-1 is by
@@ -364,12 +416,90 @@ __device__ TraceResult trace_border(const View &V, int xs, int ys, int32_t *pts)
     return R;
 }
 
+// ---- parallel tracing with checkpoints ------------------------------------------------
+// A visit of the border follower is the state (pixel c, back direction b): the next visit is
+// (c + D[s'], s' + 4) with s' the first foreground direction counter-clockwise after b.  On a
+// border every visit has b foreground and b+1 background, so visit states can be enumerated
+// from the 3x3 neighbourhood alone, and the outer border is the cycle through the start state
+// (first pixel, first foreground direction clockwise from west).  Pixels selected by a hash of
+// their coordinates become CHECKPOINTS; one thread per checkpoint follows the border to the
+// next checkpoint (a short segment), one thread links the segments starting from the start
+// state, and the segments are then written out in parallel at their offsets.
+struct Segment {
+    int len, next;
+    long long a00, a10, a01;
+};
+
+__device__ __forceinline__ bool cp_hash(int x, int y, unsigned rmask)
+{
+    unsigned h = (unsigned)x * 0x9E3779B1u ^ (unsigned)y * 0x85EBCA77u;
+    h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 13;
+    return (h & rmask) == 0;
+}
+__device__ __forceinline__ int cp_key(int lx, int ly, int b) { return ((ly << 15) | (lx << 3) | b) + 1; }
+
+__device__ __forceinline__ int ht_find(const int *keys, const int *vals, int key)
+{
+    unsigned h = ((unsigned)key * 0x9E3779B1u) >> 21; // 11 bits
+    while (true) {
+        const int k = keys[h & (TRACE_HT - 1)];
+        if (k == key) return vals[h & (TRACE_HT - 1)];
+        if (k == 0) return -1;
+        h++;
+    }
+}
+__device__ __forceinline__ void ht_insert(int *keys, int *vals, int key, int val)
+{
+    unsigned h = ((unsigned)key * 0x9E3779B1u) >> 21;
+    while (true) {
+        const int old = atomicCAS(&keys[h & (TRACE_HT - 1)], 0, key);
+        if (old == 0 || old == key) { vals[h & (TRACE_HT - 1)] = val; return; }
+        h++;
+    }
+}
+
+// Follows the border from visit (x, y, b) until the next checkpoint visit; STORE writes the
+// visited points.  Returns the id of the checkpoint reached.
+template <bool STORE>
+__device__ int trace_segment(const BitmapView &V, int x, int y, int b, unsigned rmask,
+                             const int *keys, const int *vals, Segment &S, int32_t *pts, int max_steps)
+{
+    int n = 0;
+    long long a00 = 0, a10 = 0, a01 = 0;
+    int id = -1;
+    while (n < max_steps) {
+        const unsigned nb = V.nb(x, y);
+        const unsigned rot = ((nb | (nb << 8)) >> ((b + 1) & 7)) & 0xffu;
+        const int s = (b + 1 + (__ffs(rot) - 1)) & 7;
+        const int nx = x + DIR_DX[s], ny = y + DIR_DY[s];
+        if (STORE) { pts[2 * n] = x; pts[2 * n + 1] = y; }
+        else {
+            const long long dxy = (long long)x * ny - (long long)nx * y;
+            a00 += dxy; a10 += dxy * (x + nx); a01 += dxy * (y + ny);
+        }
+        n++;
+        x = nx; y = ny; b = (s + 4) & 7;
+        if (cp_hash(x, y, rmask) || (x == V.sx && y == V.sy)) {
+            id = ht_find(keys, vals, cp_key(x - V.bx0, y - V.by0, b));
+            if (id >= 0) break;
+        }
+    }
+    if (!STORE) { S.len = n; S.next = id; S.a00 = a00; S.a10 = a10; S.a01 = a01; }
+    return id;
+}
+
 __global__ void __launch_bounds__(TRACE_THREADS)
 trace_kernel(const int32_t *labels, size_t LP, size_t labels_stream, const int32_t *comp,
              gofpid_frame_info *info, gofpid_blob *kept, int32_t *points, int max_blobs,
              int max_kept, int max_points, double area_min, int H, int W)
 {
-    extern __shared__ __align__(16) uint32_t bits[];
+    extern __shared__ __align__(16) uint32_t bits[]; // bitmap, then the tables below
+    Segment *seg = reinterpret_cast<Segment *>(bits + TRACE_SMEM_WORDS);
+    int *ht_keys = reinterpret_cast<int *>(seg + TRACE_MAX_CP);
+    int *ht_vals = ht_keys + TRACE_HT;
+    int *cp_state = ht_vals + TRACE_HT;     // packed (ly << 15 | lx << 3 | b)
+    int *cp_off = cp_state + TRACE_MAX_CP;  // output offset of the segment, -1 = not on the outer border
+    __shared__ int sh_ncp, sh_keep, sh_off;
     const int z = blockIdx.y;
     const int32_t *lab = labels + (size_t)z * labels_stream;
     gofpid_frame_info *fi = info + z;
@@ -390,48 +520,168 @@ trace_kernel(const int32_t *labels, size_t LP, size_t labels_stream, const int32
         const int root = first + 1;
 
         const int row_words = (bw + 2 + 31) / 32 + 1;
-        const bool fits = (size_t)row_words * (bh + 2) <= (size_t)TRACE_SMEM_WORDS;
-        __syncthreads(); // previous candidate's bitmap is no longer in use
-        if (fits) {
-            const int total = row_words * (bh + 2);
-            for (int i = warp; i < total; i += TRACE_THREADS / 32) {
-                const int r = i / row_words, wc = i - r * row_words;
-                const int yy = by0 - 1 + r, xx = bx0 - 1 + wc * 32 + lane;
-                const bool on = yy >= by0 && yy <= by1 && xx >= bx0 && xx <= bx1 &&
-                                lab[(size_t)yy * LP + xx] == root;
-                const unsigned w = __ballot_sync(0xffffffffu, on);
-                if (lane == 0) bits[i] = w;
+        const bool fits = (size_t)row_words * (bh + 2) <= (size_t)TRACE_SMEM_WORDS && bw < 4096 && bh < 4096;
+        __syncthreads(); // the previous candidate's smem state is no longer in use
+
+        if (!fits) {
+            // serial fallback straight from the label image (boxes beyond the smem bitmap)
+            if (tid == 0) {
+                GlobalView gv; gv.lab = lab; gv.LP = LP; gv.H = H; gv.W = W; gv.root = root;
+                TraceResult R = trace_border<false>(gv, xs, ys, nullptr);
+                if (fabs((double)R.a00) * 0.5 >= area_min) {
+                    int keep = atomicAdd(&fi->n_kept, 1);
+                    const int off = atomicAdd(&fi->n_points, R.n);
+                    if (keep >= max_kept) { atomicOr(&fi->overflow, 2); keep = -1; }
+                    else if (off + R.n > max_points) { atomicOr(&fi->overflow, 4); R.n = 0; }
+                    if (keep >= 0) {
+                        gofpid_blob *kb = kept + (size_t)z * max_kept + keep;
+                        kb->first = ys * W + xs;
+                        kb->x0 = bx0; kb->y0 = by0; kb->x1 = bx1; kb->y1 = by1;
+                        kb->area_px = cr[CR_AREA];
+                        kb->n_points = R.n; kb->point_offset = off;
+                        kb->a00 = R.a00; kb->a10 = R.a10; kb->a01 = R.a01;
+                        if (R.n > 0) trace_border<true>(gv, xs, ys, points + ((size_t)z * max_points + off) * 2);
+                    }
+                }
             }
+            continue;
+        }
+
+        // ---- stage the component as a bitmap with a 1-pixel empty frame ---------------------
+        const int total = row_words * (bh + 2);
+        for (int i = warp; i < total; i += TRACE_THREADS / 32) {
+            const int r = i / row_words, wc = i - r * row_words;
+            const int yy = by0 - 1 + r, xx = bx0 - 1 + wc * 32 + lane;
+            const bool on = yy >= by0 && yy <= by1 && xx >= bx0 && xx <= bx1 &&
+                            lab[(size_t)yy * LP + xx] == root;
+            const unsigned w = __ballot_sync(0xffffffffu, on);
+            if (lane == 0) bits[i] = w;
+        }
+        BitmapView bv; bv.bits = bits; bv.row_words = row_words; bv.bx0 = bx0; bv.by0 = by0;
+        bv.sx = xs; bv.sy = ys;
+        __syncthreads();
+
+        // ---- start state ------------------------------------------------------------------------
+        const unsigned nb0 = bv.nb(xs, ys);
+        int b0 = -1;
+#pragma unroll
+        for (int k = 3; k >= -3; k--) { // first foreground neighbour clockwise from west
+            const int d = k & 7;
+            if (b0 < 0 && ((nb0 >> d) & 1u)) b0 = d;
+        }
+        if (b0 < 0) { // isolated pixel: a one-point contour of area 0
+            if (tid == 0 && 0.0 >= area_min) {
+                int keep = atomicAdd(&fi->n_kept, 1);
+                const int off = atomicAdd(&fi->n_points, 1);
+                if (keep >= max_kept) { atomicOr(&fi->overflow, 2); keep = -1; }
+                else if (off + 1 > max_points) { atomicOr(&fi->overflow, 4); keep = -2; }
+                if (keep >= 0) {
+                    gofpid_blob *kb = kept + (size_t)z * max_kept + keep;
+                    kb->first = ys * W + xs; kb->x0 = bx0; kb->y0 = by0; kb->x1 = bx1; kb->y1 = by1;
+                    kb->area_px = cr[CR_AREA]; kb->n_points = 1; kb->point_offset = off;
+                    kb->a00 = 0; kb->a10 = 0; kb->a01 = 0;
+                    int32_t *dst = points + ((size_t)z * max_points + off) * 2;
+                    dst[0] = xs; dst[1] = ys;
+                }
+            }
+            continue;
+        }
+
+        // ---- enumerate checkpoints (retry with a sparser hash when there are too many) -----------
+        unsigned rmask = 3u;
+        {
+            const int est = 2 * (bw + bh);
+            while ((int)(rmask + 1) * (TRACE_MAX_CP / 2) < est) rmask = (rmask << 1) | 1u;
+        }
+        while (true) {
+            for (int i = tid; i < TRACE_HT; i += TRACE_THREADS) ht_keys[i] = 0;
+            if (tid == 0) {
+                sh_ncp = 1;
+                cp_state[0] = ((ys - by0) << 15) | ((xs - bx0) << 3) | b0;
+            }
+            __syncthreads();
+            if (tid == 0) ht_insert(ht_keys, ht_vals, cp_key(xs - bx0, ys - by0, b0), 0);
+            for (int i = tid; i < bw * bh; i += TRACE_THREADS) {
+                const int ly = i / bw, lx = i - ly * bw;
+                const int x = bx0 + lx, y = by0 + ly;
+                if (!cp_hash(x, y, rmask)) continue;
+                // is the pixel part of the component?
+                const int bx = lx + 1;
+                if (!((bits[(size_t)(ly + 1) * row_words + (bx >> 5)] >> (bx & 31)) & 1u)) continue;
+                const unsigned nb = bv.nb(x, y);
+                // visit states: direction b foreground, b+1 background
+                unsigned starts = nb & ~((nb >> 1) | (nb << 7)) & 0xffu;
+                while (starts) {
+                    const int b = __ffs(starts) - 1;
+                    starts &= starts - 1;
+                    if (x == xs && y == ys && b == b0) continue; // already checkpoint 0
+                    const int id = atomicAdd(&sh_ncp, 1);
+                    if (id < TRACE_MAX_CP) {
+                        cp_state[id] = (ly << 15) | (lx << 3) | b;
+                        ht_insert(ht_keys, ht_vals, cp_key(lx, ly, b), id);
+                    }
+                }
+            }
+            __syncthreads();
+            if (sh_ncp <= TRACE_MAX_CP) break;
+            rmask = (rmask << 1) | 1u; // too many: halve the density and start over
+            __syncthreads();
+        }
+        const int ncp = sh_ncp;
+
+        // ---- pass 1: every checkpoint follows the border to the next checkpoint -------------------
+        const int max_steps = 4 * bw * bh + 16;
+        for (int i = tid; i < ncp; i += TRACE_THREADS) {
+            const int st = cp_state[i];
+            Segment S;
+            trace_segment<false>(bv, bx0 + ((st >> 3) & 4095), by0 + (st >> 15), st & 7, rmask, ht_keys,
+                                 ht_vals, S, nullptr, max_steps);
+            seg[i] = S;
+            cp_off[i] = -1;
         }
         __syncthreads();
+
+        // ---- link the segments of the outer border, starting from the start state -----------------
         if (tid == 0) {
-            TraceResult R;
-            // bitmap (0, 0) is image (bx0-1, by0-1), so the 3x3 window of (x, y) starts at
-            // bitmap column x - bx0, row y - by0
-            BitmapView bv; bv.bits = bits; bv.row_words = row_words; bv.bx0 = bx0; bv.by0 = by0;
-            GlobalView gv; gv.lab = lab; gv.LP = LP; gv.H = H; gv.W = W; gv.root = root;
-            if (fits) R = trace_border<false>(bv, xs, ys, nullptr);
-            else R = trace_border<false>(gv, xs, ys, nullptr);
-            const double area = fabs((double)R.a00) * 0.5;
-            int keep = -1, off = 0;
-            if (area >= area_min) {
+            int id = 0, off = 0, guard = 0;
+            long long a00 = 0, a10 = 0, a01 = 0;
+            do {
+                cp_off[id] = off;
+                off += seg[id].len;
+                a00 += seg[id].a00; a10 += seg[id].a10; a01 += seg[id].a01;
+                id = seg[id].next;
+            } while (id > 0 && ++guard < ncp);
+            int keep = -1, base = 0;
+            if (id != 0) atomicOr(&fi->overflow, 8); // border did not close: internal error
+            if (id == 0 && fabs((double)a00) * 0.5 >= area_min) {
                 keep = atomicAdd(&fi->n_kept, 1);
-                off = atomicAdd(&fi->n_points, R.n);
+                base = atomicAdd(&fi->n_points, off);
                 if (keep >= max_kept) { atomicOr(&fi->overflow, 2); keep = -1; }
-                else if (off + R.n > max_points) { atomicOr(&fi->overflow, 4); R.n = 0; }
-                if (keep >= 0) {
+                else {
+                    int npts = off;
+                    if (base + off > max_points) { atomicOr(&fi->overflow, 4); npts = 0; }
                     gofpid_blob *kb = kept + (size_t)z * max_kept + keep;
                     kb->first = ys * W + xs;
                     kb->x0 = bx0; kb->y0 = by0; kb->x1 = bx1; kb->y1 = by1;
                     kb->area_px = cr[CR_AREA];
-                    kb->n_points = R.n; kb->point_offset = off;
-                    kb->a00 = R.a00; kb->a10 = R.a10; kb->a01 = R.a01;
-                    if (R.n > 0) {
-                        int32_t *dst = points + ((size_t)z * max_points + off) * 2;
-                        if (fits) trace_border<true>(bv, xs, ys, dst);
-                        else trace_border<true>(gv, xs, ys, dst);
-                    }
+                    kb->n_points = npts; kb->point_offset = base;
+                    kb->a00 = a00; kb->a10 = a10; kb->a01 = a01;
+                    if (npts == 0) keep = -1;
                 }
+            }
+            sh_keep = keep; sh_off = base;
+        }
+        __syncthreads();
+
+        // ---- pass 2: write the contour, one thread per linked segment -----------------------------
+        if (sh_keep >= 0) {
+            int32_t *dst = points + ((size_t)z * max_points + sh_off) * 2;
+            for (int i = tid; i < ncp; i += TRACE_THREADS) {
+                if (cp_off[i] < 0) continue;
+                const int st = cp_state[i];
+                Segment S;
+                trace_segment<true>(bv, bx0 + ((st >> 3) & 4095), by0 + (st >> 15), st & 7, rmask, ht_keys,
+                                    ht_vals, S, dst + 2 * (size_t)cp_off[i], max_steps);
             }
         }
     }
@@ -445,7 +695,7 @@ static int launch_labelling(ImageU8 mask, int32_t *labels, size_t LP, size_t lab
                             cudaStream_t s)
 {
     const dim3 tgrid((W + CCL_TW - 1) / CCL_TW, (H + CCL_TH - 1) / CCL_TH, n_streams);
-    label_tiles_kernel<<<tgrid, dim3(32, CCL_TH), 0, s>>>(mask, labels, LP, labels_stream, H, W,
+    label_tiles_kernel<<<tgrid, dim3(16, CCL_TH), 0, s>>>(mask, labels, LP, labels_stream, H, W,
                                                           info, tick);
     GOFPID_CUDA_TRY(cudaGetLastError());
     merge_tiles_kernel<<<tgrid, CCL_TW + 2 * CCL_TH, 0, s>>>(mask, labels, LP, labels_stream, H, W);
@@ -466,9 +716,9 @@ int launch_blobs(const BlobBuffers &B, ImageU8 mask, int H, int W, int n_streams
                                                B.slot, B.comp, B.max_blobs, H, W);
     GOFPID_CUDA_TRY(cudaGetLastError());
     GOFPID_CUDA_TRY(cudaFuncSetAttribute(trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         TRACE_SMEM_WORDS * 4));
-    const dim3 cgrid(n_streams >= 32 ? 8 : 64, n_streams);
-    trace_kernel<<<cgrid, TRACE_THREADS, TRACE_SMEM_WORDS * 4, s>>>(
+                                         (int)TRACE_SMEM_BYTES));
+    const dim3 cgrid(n_streams >= 32 ? 8 : (n_streams >= 4 ? 32 : 128), n_streams);
+    trace_kernel<<<cgrid, TRACE_THREADS, TRACE_SMEM_BYTES, s>>>(
         B.labels, B.labels_pitch, B.labels_stream, B.comp, B.info, B.kept, B.points, B.max_blobs,
         B.max_kept, B.max_points, B.area_min, H, W);
     GOFPID_CUDA_TRY(cudaGetLastError());
