@@ -30,12 +30,12 @@ constexpr int CCL_TW = 64;  // one 64-bit word of class bits per tile row
 constexpr int CCL_TH = 32;
 constexpr int CCL_THREADS = 16 * CCL_TH; // each thread owns 4 consecutive pixels of a row
 
-constexpr int TRACE_THREADS = 256;
-constexpr int TRACE_SMEM_WORDS = 32 * 1024; // 128 KB bitmap: boxes up to ~1 Mpx
-constexpr int TRACE_MAX_CP = 1024;          // checkpoints per contour
-constexpr int TRACE_HT = 2048;              // hash slots (power of two, >= 2 * TRACE_MAX_CP)
-constexpr size_t TRACE_SMEM_BYTES = (size_t)TRACE_SMEM_WORDS * 4 + (size_t)TRACE_MAX_CP * (32 + 8) +
-                                    (size_t)TRACE_HT * 8;
+constexpr int TRACE_THREADS = 1024;
+constexpr int TRACE_MAX_CP = 4096;          // checkpoints per contour
+constexpr int TRACE_HT = 8192;              // hash slots (power of two, >= 2 * TRACE_MAX_CP)
+constexpr int TRACE_HT_SHIFT = 19;          // 32 - log2(TRACE_HT)
+// per checkpoint: a00 (8 B) + state, length, two (next, distance) pairs (24 B)
+constexpr size_t TRACE_SMEM_BYTES = (size_t)TRACE_MAX_CP * (8 + 24) + (size_t)TRACE_HT * 8;
 
 // component record layout (8 int32)
 enum { CR_FIRST = 0, CR_X0, CR_Y0, CR_X1, CR_Y1, CR_AREA, CR_PAD0, CR_PAD1, CR_SIZE };
@@ -146,15 +146,20 @@ label_tiles_kernel(ImageU8 mask, int32_t *labels, size_t LP, size_t labels_strea
     if (ty > 0) { Fp = ((unsigned long long)Fw[ty - 1][1] << 32) | Fw[ty - 1][0]; Vp = V; }
 
     // provisional labels: every pixel points at its run start; a background run that touches
-    // the frame border is the virtual OUTSIDE node (0)
+    // the frame border is the virtual OUTSIDE node (0).  The four pixels of a thread mostly
+    // share a run, so the 64-bit run searches are done once per run, not once per pixel.
+    int ra[4]; // run start column of each pixel (-1: outside the image)
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const int c = lx + j;
         const int li = ty * CCL_TW + c;
-        if (!row_ok || c >= wvalid) { lab[li] = li + 1; continue; }
+        if (!row_ok || c >= wvalid) { ra[j] = -1; lab[li] = li + 1; continue; }
         const bool fg = (F >> c) & 1ULL;
         const unsigned long long S = fg ? F : (~F & V);
-        const int a = run_start(S, c);
+        int a;
+        if (j > 0 && ra[j - 1] >= 0 && (((F >> (c - 1)) & 1ULL) != 0) == fg) a = ra[j - 1];
+        else a = run_start(S, c);
+        ra[j] = a;
         int v = ty * CCL_TW + a + 1;
         if (a == c && !fg) {
             const int b = run_end(S, c);
@@ -169,10 +174,9 @@ label_tiles_kernel(ImageU8 mask, int32_t *labels, size_t LP, size_t labels_strea
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int c = lx + j;
-            if (c >= wvalid) continue;
+            if (ra[j] != c) continue; // not a run start (or outside the image)
             const bool fg = (F >> c) & 1ULL;
             const unsigned long long S = fg ? F : (~F & V);
-            if (run_start(S, c) != c) continue;
             const int b = run_end(S, c);
             const unsigned long long Sp = fg ? Fp : (~Fp & Vp);
             const int lo = fg ? max(c - 1, 0) : c, hi = fg ? min(b + 1, 63) : b;
@@ -188,13 +192,28 @@ label_tiles_kernel(ImageU8 mask, int32_t *labels, size_t LP, size_t labels_strea
     }
     __syncthreads();
 
+    // compress: every run start learns its root (read phase, barrier, write phase), so the
+    // per-pixel lookups below are a single hop
+    int rr[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        rr[j] = -1;
+        if (ra[j] == lx + j) rr[j] = uf_find(lab, ty * CCL_TW + lx + j + 1);
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        if (rr[j] >= 0) lab[ty * CCL_TW + lx + j] = rr[j];
+    __syncthreads();
+
     if (y >= H || x >= W) return;
     int out[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        const int r = uf_find(lab, ty * CCL_TW + lx + j + 1);
-        out[j] = r == 0 ? 0
-                        : (int)((size_t)(y0 + (r - 1) / CCL_TW) * LP + x0 + (r - 1) % CCL_TW) + 1;
+        if (ra[j] < 0) { out[j] = 0; continue; }
+        if (j > 0 && ra[j] == ra[j - 1]) { out[j] = out[j - 1]; continue; }
+        const int r = lab[ty * CCL_TW + ra[j]]; // root of the run start (0 = OUTSIDE)
+        out[j] = r == 0 ? 0 : (int)((size_t)(y0 + (r - 1) / CCL_TW) * LP + x0 + (r - 1) % CCL_TW) + 1;
     }
     int32_t *lrow = labels + (size_t)blockIdx.z * labels_stream + (size_t)y * LP;
     *reinterpret_cast<int4 *>(lrow + x) = make_int4(out[0], out[1], out[2], out[3]);
@@ -237,22 +256,30 @@ merge_tiles_kernel(ImageU8 mask, int32_t *labels, size_t LP, size_t labels_strea
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 flatten_kernel(ImageU8 mask, int32_t *labels, size_t LP, size_t labels_stream, int32_t *slot,
-               int32_t *comp, gofpid_frame_info *info, int max_blobs, int H, int W)
+               int32_t *comp, gofpid_frame_info *info, int max_blobs, uint32_t *bitimg,
+               int bit_pitch, size_t bit_stream, int H, int W)
 {
     const int x = (blockIdx.x * 32 + threadIdx.x) * 4, y = blockIdx.y * 8 + threadIdx.y;
-    if (y >= H || x >= W) return;
+    if (y >= H) return; // warp-uniform: a warp is one row of 128 pixels
     int32_t *lab = labels + (size_t)blockIdx.z * labels_stream;
     const uint8_t *mrow = mask.base + (size_t)blockIdx.z * mask.stream_stride + (size_t)y * mask.pitch;
-    const uint32_t mw = *reinterpret_cast<const uint32_t *>(mrow + x);
-    int4 v4 = *reinterpret_cast<const int4 *>(lab + (size_t)y * LP + x);
-    int v[4] = {v4.x, v4.y, v4.z, v4.w};
+    uint32_t mw = 0;
+    int v[4] = {0, 0, 0, 0};
+    if (x < W) {
+        mw = *reinterpret_cast<const uint32_t *>(mrow + x);
+        const int4 v4 = *reinterpret_cast<const int4 *>(lab + (size_t)y * LP + x);
+        v[0] = v4.x; v[1] = v4.y; v[2] = v4.z; v[3] = v4.w;
+    }
+    unsigned nib = 0;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         if (x + j >= W) continue;
+        const bool fg = ((mw >> (8 * j)) & 255) != 0;
+        if (fg) nib |= 1u << j;
         const int self = (int)((size_t)y * LP + x + j) + 1;
         const int r = uf_find_g(lab, v[j]);
         v[j] = r;
-        if (r == self && ((mw >> (8 * j)) & 255) != 0) {
+        if (r == self && fg) {
             gofpid_frame_info *fi = info + blockIdx.z;
             const int s = atomicAdd(&fi->n_components, 1);
             int32_t *sl = slot + (size_t)blockIdx.z * LP * H;
@@ -267,9 +294,15 @@ flatten_kernel(ImageU8 mask, int32_t *labels, size_t LP, size_t labels_stream, i
             }
         }
     }
+    // foreground bit image for the border tracer: pixel (x, y) is bit x + 32 of row y + 1
+    // (one guard word left / right and one guard row above / below stay zero)
+    const unsigned lane = threadIdx.x;
+    const unsigned word = __reduce_or_sync(0xffu << (lane & 24), nib << (4 * (lane & 7)));
+    if ((lane & 7) == 0 && x < W)
+        bitimg[(size_t)blockIdx.z * bit_stream + (size_t)(y + 1) * bit_pitch + 1 + (x >> 5)] = word;
     // roots are final here (merging finished with the previous kernel), so writing the root
     // over a non-root entry only shortens paths other threads may still be walking
-    *reinterpret_cast<int4 *>(lab + (size_t)y * LP + x) = make_int4(v[0], v[1], v[2], v[3]);
+    if (x < W) *reinterpret_cast<int4 *>(lab + (size_t)y * LP + x) = make_int4(v[0], v[1], v[2], v[3]);
 }
 
 // ------------------------------------------------------------------------------------
@@ -327,94 +360,36 @@ stats_kernel(ImageU8 mask, const int32_t *labels, size_t LP, size_t labels_strea
 // 5. outer-border tracing
 // ------------------------------------------------------------------------------------
 // direction codes: 0=E 1=NE 2=N 3=NW 4=W 5=SW 6=S 7=SE (y grows downwards)
-__device__ __constant__ int8_t DIR_DX[8] = {1, 1, 0, -1, -1, -1, 0, 1};
-__device__ __constant__ int8_t DIR_DY[8] = {0, -1, -1, -1, 0, 1, 1, 1};
+// dx + 1 and dy + 1 of the 8 directions, two bits each
+#define DIR_DX_LUT 0x901au /* dx+1 of E NE N NW W SW S SE = 2 2 1 0 0 0 1 2 */
+#define DIR_DY_LUT 0xa901u /* dy+1 of E NE N NW W SW S SE = 1 0 0 0 1 2 2 2 */
+__device__ __forceinline__ int dir_dx(int d) { return (int)((DIR_DX_LUT >> (2 * d)) & 3u) - 1; }
+__device__ __forceinline__ int dir_dy(int d) { return (int)((DIR_DY_LUT >> (2 * d)) & 3u) - 1; }
 
-struct BitmapView { // component staged in smem with a 1-pixel empty frame
-    const uint32_t *bits;
-    int row_words;
-    int bx0, by0; // image coords of bitmap (1, 1)
-    int sx, sy;   // the component's first pixel (start of the border)
+// 3x3 neighbourhood of (x, y) from the foreground bit image as 8 ring bits (bit d = direction d)
+struct BitView {
+    const uint32_t *img; // stream's bit image
+    int pitch;           // words per row
     __device__ __forceinline__ unsigned nb(int x, int y) const
     {
-        const int bx = x - bx0, by = y - by0; // bitmap column of x-1 is bx, row of y-1 is by
-        const int w = bx >> 5, sh = bx & 31;
-        const uint32_t *r = bits + (size_t)by * row_words + w;
-        const unsigned t = __funnelshift_r(r[0], r[1], sh) & 7u;
-        const unsigned m = __funnelshift_r(r[row_words], r[row_words + 1], sh) & 7u;
-        const unsigned b = __funnelshift_r(r[2 * row_words], r[2 * row_words + 1], sh) & 7u;
+        const int p = x + 31;                       // bit position of x - 1
+        const uint32_t *r = img + (size_t)y * pitch + (p >> 5); // row of y - 1
+        const int sh = p & 31;
+        const unsigned t = __funnelshift_r(__ldg(r), __ldg(r + 1), sh) & 7u;
+        const unsigned m = __funnelshift_r(__ldg(r + pitch), __ldg(r + pitch + 1), sh) & 7u;
+        const unsigned b = __funnelshift_r(__ldg(r + 2 * pitch), __ldg(r + 2 * pitch + 1), sh) & 7u;
         return ((m >> 2) & 1u) | (((t >> 2) & 1u) << 1) | (((t >> 1) & 1u) << 2) | ((t & 1u) << 3) |
                ((m & 1u) << 4) | ((b & 1u) << 5) | (((b >> 1) & 1u) << 6) | (((b >> 2) & 1u) << 7);
     }
 };
-struct GlobalView { // fallback for components whose box does not fit in shared memory
-    const int32_t *lab;
-    size_t LP;
-    int H, W, root;
-    __device__ __forceinline__ unsigned nb(int x, int y) const
-    {
-        unsigned r = 0;
-#pragma unroll
-        for (int d = 0; d < 8; d++) {
-            const int xx = x + DIR_DX[d], yy = y + DIR_DY[d];
-            if (xx >= 0 && xx < W && yy >= 0 && yy < H && lab[(size_t)yy * LP + xx] == root)
-                r |= 1u << d;
-        }
-        return r;
-    }
-};
 
-struct TraceResult {
-    int n;
-    long long a00, a10, a01;
-};
-
-// Follows the outer border from the component's raster-first pixel (xs, ys) the way
-// cv.findContours does for an outer border.  STORE: write the points, else only count and
-// accumulate the Green sums of cv.contourArea / cv.moments.
-template <bool STORE, typename View>
-__device__ TraceResult trace_border(const View &V, int xs, int ys, int32_t *pts)
-{
-    TraceResult R; R.n = 0; R.a00 = 0; R.a10 = 0; R.a01 = 0;
-    // first neighbour clockwise from west
-    const unsigned nb0 = V.nb(xs, ys);
-    int s = -1;
-#pragma unroll
-    for (int k = 3; k >= -3; k--) { // 3,2,1,0,7,6,5
-        const int d = k & 7;
-        if (s < 0 && ((nb0 >> d) & 1u)) s = d;
-    }
-    if (s < 0) { // isolated pixel
-        if (STORE) { pts[0] = xs; pts[1] = ys; }
-        R.n = 1;
-        return R;
-    }
-    const int x1 = xs + DIR_DX[s], y1 = ys + DIR_DY[s];
-    int cx = xs, cy = ys;
-    int px = 0, py = 0; // previous emitted point
-    while (true) {
-        const unsigned nb = V.nb(cx, cy);
-        // counter-clockwise search starting after the direction we came from
-        const unsigned rot = ((nb | (nb << 8)) >> ((s + 1) & 7)) & 0xffu;
-        s = (s + 1 + (__ffs(rot) - 1)) & 7;
-        const int nx = cx + DIR_DX[s], ny = cy + DIR_DY[s];
-        if (STORE) { pts[2 * R.n] = cx; pts[2 * R.n + 1] = cy; }
-        else if (R.n > 0) {
-            const long long dxy = (long long)px * cy - (long long)cx * py;
-            R.a00 += dxy; R.a10 += dxy * (px + cx); R.a01 += dxy * (py + cy);
-        }
-        px = cx; py = cy;
-        R.n++;
-        if (nx == xs && ny == ys && cx == x1 && cy == y1) break;
-        cx = nx; cy = ny;
-        s = (s + 4) & 7;
-    }
-    if (!STORE) { // closing edge: last point -> first point
-        const long long dxy = (long long)px * ys - (long long)xs * py;
-        R.a00 += dxy; R.a10 += dxy * (px + xs); R.a01 += dxy * (py + ys);
-    }
-    return R;
-}
+#ifdef GOFPID_TRACE_DEBUG
+__device__ long long g_trace_dbg[64 * 16];
+__device__ int g_trace_dbg_n;
+#define DBG_T(k) if (threadIdx.x == 0) dbg_t[k] = clock64()
+#else
+#define DBG_T(k)
+#endif
 
 // ---- parallel tracing with checkpoints ------------------------------------------------
 // A visit of the border follower is the state (pixel c, back direction b): the next visit is
@@ -423,24 +398,20 @@ __device__ TraceResult trace_border(const View &V, int xs, int ys, int32_t *pts)
 // from the 3x3 neighbourhood alone, and the outer border is the cycle through the start state
 // (first pixel, first foreground direction clockwise from west).  Pixels selected by a hash of
 // their coordinates become CHECKPOINTS; one thread per checkpoint follows the border to the
-// next checkpoint (a short segment), one thread links the segments starting from the start
-// state, and the segments are then written out in parallel at their offsets.
-struct Segment {
-    int len, next;
-    long long a00, a10, a01;
-};
-
+// next checkpoint (a short segment), the segments are ranked along the cycle by pointer
+// jumping, and then written out in parallel at their offsets.  Tracing reads the frame's
+// foreground bit image (L1-resident around a blob), so any blob size is handled alike.
 __device__ __forceinline__ bool cp_hash(int x, int y, unsigned rmask)
 {
     unsigned h = (unsigned)x * 0x9E3779B1u ^ (unsigned)y * 0x85EBCA77u;
     h ^= h >> 15; h *= 0x2C1B3C6Du; h ^= h >> 13;
     return (h & rmask) == 0;
 }
-__device__ __forceinline__ int cp_key(int lx, int ly, int b) { return ((ly << 15) | (lx << 3) | b) + 1; }
+__device__ __forceinline__ int cp_key(int x, int y, int b) { return ((y << 16) | (x << 3) | b) + 1; }
 
 __device__ __forceinline__ int ht_find(const int *keys, const int *vals, int key)
 {
-    unsigned h = ((unsigned)key * 0x9E3779B1u) >> 21; // 11 bits
+    unsigned h = ((unsigned)key * 0x9E3779B1u) >> TRACE_HT_SHIFT;
     while (true) {
         const int k = keys[h & (TRACE_HT - 1)];
         if (k == key) return vals[h & (TRACE_HT - 1)];
@@ -450,7 +421,7 @@ __device__ __forceinline__ int ht_find(const int *keys, const int *vals, int key
 }
 __device__ __forceinline__ void ht_insert(int *keys, int *vals, int key, int val)
 {
-    unsigned h = ((unsigned)key * 0x9E3779B1u) >> 21;
+    unsigned h = ((unsigned)key * 0x9E3779B1u) >> TRACE_HT_SHIFT;
     while (true) {
         const int old = atomicCAS(&keys[h & (TRACE_HT - 1)], 0, key);
         if (old == 0 || old == key) { vals[h & (TRACE_HT - 1)] = val; return; }
@@ -458,53 +429,68 @@ __device__ __forceinline__ void ht_insert(int *keys, int *vals, int key, int val
     }
 }
 
-// Follows the border from visit (x, y, b) until the next checkpoint visit; STORE writes the
-// visited points.  Returns the id of the checkpoint reached.
+struct SegSums { long long a00, a10, a01; };
+
+// Follows the border from visit (x, y, b) until the next checkpoint visit.  STORE writes the
+// visited points, otherwise the Green sums of cv.contourArea / cv.moments are accumulated
+// (a step from p to q contributes dxy = p.x*q.y - q.x*p.y, dxy*(p.x+q.x), dxy*(p.y+q.y)).
+// Returns the id of the checkpoint reached (-1: none within max_steps).
 template <bool STORE>
-__device__ int trace_segment(const BitmapView &V, int x, int y, int b, unsigned rmask,
-                             const int *keys, const int *vals, Segment &S, int32_t *pts, int max_steps)
+__device__ int trace_segment(const BitView &V, int x, int y, int b, int xs, int ys, unsigned rmask,
+                             const int *keys, const int *vals, int &len, SegSums &S, int32_t *pts,
+                             int max_steps)
 {
-    int n = 0;
+    int n = 0, id = -1;
     long long a00 = 0, a10 = 0, a01 = 0;
-    int id = -1;
     while (n < max_steps) {
         const unsigned nb = V.nb(x, y);
         const unsigned rot = ((nb | (nb << 8)) >> ((b + 1) & 7)) & 0xffu;
         const int s = (b + 1 + (__ffs(rot) - 1)) & 7;
-        const int nx = x + DIR_DX[s], ny = y + DIR_DY[s];
-        if (STORE) { pts[2 * n] = x; pts[2 * n + 1] = y; }
-        else {
-            const long long dxy = (long long)x * ny - (long long)nx * y;
-            a00 += dxy; a10 += dxy * (x + nx); a01 += dxy * (y + ny);
+        const int dx = dir_dx(s), dy = dir_dy(s);
+        const int dxy = x * dy - y * dx; // = x*(y+dy) - (x+dx)*y
+        if (STORE) {
+            *reinterpret_cast<int2 *>(pts + 2 * n) = make_int2(x, y);
+            a10 += (long long)dxy * (2 * x + dx); a01 += (long long)dxy * (2 * y + dy);
+        } else {
+            a00 += dxy;
         }
         n++;
-        x = nx; y = ny; b = (s + 4) & 7;
-        if (cp_hash(x, y, rmask) || (x == V.sx && y == V.sy)) {
-            id = ht_find(keys, vals, cp_key(x - V.bx0, y - V.by0, b));
+        x += dx; y += dy; b = (s + 4) & 7;
+        if (cp_hash(x, y, rmask) || (x == xs && y == ys)) {
+            id = ht_find(keys, vals, cp_key(x, y, b));
             if (id >= 0) break;
         }
     }
-    if (!STORE) { S.len = n; S.next = id; S.a00 = a00; S.a10 = a10; S.a01 = a01; }
+    len = n;
+    S.a00 = a00; S.a10 = a10; S.a01 = a01;
     return id;
 }
 
 __global__ void __launch_bounds__(TRACE_THREADS)
 trace_kernel(const int32_t *labels, size_t LP, size_t labels_stream, const int32_t *comp,
              gofpid_frame_info *info, gofpid_blob *kept, int32_t *points, int max_blobs,
-             int max_kept, int max_points, double area_min, int H, int W)
+             int max_kept, int max_points, double area_min, const uint32_t *bitimg, int bit_pitch,
+             size_t bit_stream, int H, int W)
 {
-    extern __shared__ __align__(16) uint32_t bits[]; // bitmap, then the tables below
-    Segment *seg = reinterpret_cast<Segment *>(bits + TRACE_SMEM_WORDS);
-    int *ht_keys = reinterpret_cast<int *>(seg + TRACE_MAX_CP);
+    extern __shared__ __align__(16) unsigned char tsm[];
+    long long *seg_a00 = reinterpret_cast<long long *>(tsm);             // per checkpoint
+    int *ht_keys = reinterpret_cast<int *>(seg_a00 + TRACE_MAX_CP);
     int *ht_vals = ht_keys + TRACE_HT;
-    int *cp_state = ht_vals + TRACE_HT;     // packed (ly << 15 | lx << 3 | b)
-    int *cp_off = cp_state + TRACE_MAX_CP;  // output offset of the segment, -1 = not on the outer border
+    int *cp_state = ht_vals + TRACE_HT;   // packed (y << 16 | x << 3 | b)
+    int *seg_len = cp_state + TRACE_MAX_CP;
+    int *nxtA = seg_len + TRACE_MAX_CP;
+    int *nxtB = nxtA + TRACE_MAX_CP;
+    unsigned *dA = reinterpret_cast<unsigned *>(nxtB + TRACE_MAX_CP);
+    unsigned *dB = dA + TRACE_MAX_CP;
     __shared__ int sh_ncp, sh_keep, sh_off;
+    __shared__ int sh_warp[32];
+    __shared__ long long sh_part[3][32];
     const int z = blockIdx.y;
     const int32_t *lab = labels + (size_t)z * labels_stream;
     gofpid_frame_info *fi = info + z;
     const int ncomp = min(fi->n_components, max_blobs);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int tid = threadIdx.x;
+    BitView bv; bv.img = bitimg + (size_t)z * bit_stream; bv.pitch = bit_pitch;
 
     for (int ci = blockIdx.x; ci < ncomp; ci += gridDim.x) {
         const int32_t *cr = comp + ((size_t)z * max_blobs + ci) * CR_SIZE;
@@ -517,49 +503,11 @@ trace_kernel(const int32_t *labels, size_t LP, size_t labels_stream, const int32
         // RETR_EXTERNAL: the background left of the first pixel must reach the frame border
         if (xs > 0 && lab[first - 1] != 0) continue;
         if (tid == 0) atomicAdd(&fi->n_candidates, 1);
-        const int root = first + 1;
-
-        const int row_words = (bw + 2 + 31) / 32 + 1;
-        const bool fits = (size_t)row_words * (bh + 2) <= (size_t)TRACE_SMEM_WORDS && bw < 4096 && bh < 4096;
-        __syncthreads(); // the previous candidate's smem state is no longer in use
-
-        if (!fits) {
-            // serial fallback straight from the label image (boxes beyond the smem bitmap)
-            if (tid == 0) {
-                GlobalView gv; gv.lab = lab; gv.LP = LP; gv.H = H; gv.W = W; gv.root = root;
-                TraceResult R = trace_border<false>(gv, xs, ys, nullptr);
-                if (fabs((double)R.a00) * 0.5 >= area_min) {
-                    int keep = atomicAdd(&fi->n_kept, 1);
-                    const int off = atomicAdd(&fi->n_points, R.n);
-                    if (keep >= max_kept) { atomicOr(&fi->overflow, 2); keep = -1; }
-                    else if (off + R.n > max_points) { atomicOr(&fi->overflow, 4); R.n = 0; }
-                    if (keep >= 0) {
-                        gofpid_blob *kb = kept + (size_t)z * max_kept + keep;
-                        kb->first = ys * W + xs;
-                        kb->x0 = bx0; kb->y0 = by0; kb->x1 = bx1; kb->y1 = by1;
-                        kb->area_px = cr[CR_AREA];
-                        kb->n_points = R.n; kb->point_offset = off;
-                        kb->a00 = R.a00; kb->a10 = R.a10; kb->a01 = R.a01;
-                        if (R.n > 0) trace_border<true>(gv, xs, ys, points + ((size_t)z * max_points + off) * 2);
-                    }
-                }
-            }
-            continue;
-        }
-
-        // ---- stage the component as a bitmap with a 1-pixel empty frame ---------------------
-        const int total = row_words * (bh + 2);
-        for (int i = warp; i < total; i += TRACE_THREADS / 32) {
-            const int r = i / row_words, wc = i - r * row_words;
-            const int yy = by0 - 1 + r, xx = bx0 - 1 + wc * 32 + lane;
-            const bool on = yy >= by0 && yy <= by1 && xx >= bx0 && xx <= bx1 &&
-                            lab[(size_t)yy * LP + xx] == root;
-            const unsigned w = __ballot_sync(0xffffffffu, on);
-            if (lane == 0) bits[i] = w;
-        }
-        BitmapView bv; bv.bits = bits; bv.row_words = row_words; bv.bx0 = bx0; bv.by0 = by0;
-        bv.sx = xs; bv.sy = ys;
-        __syncthreads();
+#ifdef GOFPID_TRACE_DEBUG
+        long long dbg_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#endif
+        DBG_T(0);
+        __syncthreads(); // the previous candidate's tables are no longer in use
 
         // ---- start state ------------------------------------------------------------------------
         const unsigned nb0 = bv.nb(xs, ys);
@@ -588,104 +536,261 @@ trace_kernel(const int32_t *labels, size_t LP, size_t labels_stream, const int32
         }
 
         // ---- enumerate checkpoints (retry with a sparser hash when there are too many) -----------
-        unsigned rmask = 3u;
+        unsigned rmask = 0u; // every visit is a checkpoint unless the border is very long
         {
             const int est = 2 * (bw + bh);
             while ((int)(rmask + 1) * (TRACE_MAX_CP / 2) < est) rmask = (rmask << 1) | 1u;
         }
+        const int w0 = (bx0 + 32) >> 5, w1 = (bx1 + 32) >> 5, wpr = w1 - w0 + 1; // bit-image words of the box
+        // Balanced enumeration in three phases, each followed by a block-wide scan instead of a
+        // contended counter: (A) per bit-image word, the hash-selected border pixels go to a
+        // compact candidate list; (B) one thread per candidate counts its visit states;
+        // (C) the states are written to their slots and entered in the hash table.
+        int *cand_list = nxtA; // the ranking arrays are free until pass 1: 4 * TRACE_MAX_CP ints
+        constexpr int CAND_CAP = 4 * TRACE_MAX_CP;
+        auto block_scan = [&](int mine, int &total) -> int { // exclusive prefix of `mine`
+            int incl = mine;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, incl, o);
+                if ((tid & 31) >= o) incl += t;
+            }
+            __syncthreads(); // sh_warp may still be read from the previous scan
+            if ((tid & 31) == 31) sh_warp[tid >> 5] = incl;
+            __syncthreads();
+            if (tid < 32) {
+                int v = tid < TRACE_THREADS / 32 ? sh_warp[tid] : 0;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const int t = __shfl_up_sync(0xffffffffu, v, o);
+                    if (tid >= o) v += t;
+                }
+                sh_warp[tid] = v; // inclusive totals per warp
+            }
+            __syncthreads();
+            total = sh_warp[31];
+            return ((tid >> 5) ? sh_warp[(tid >> 5) - 1] : 0) + incl - mine;
+        };
+        // hash-selected border pixels of one bit-image word of the box
+        auto word_cands = [&](int i, int &y, int &xw) -> uint32_t {
+            const int ry = i / wpr, wc = w0 + (i - ry * wpr);
+            y = by0 + ry; xw = (wc << 5) - 32;
+            const uint32_t *r = bv.img + (size_t)y * bv.pitch + wc; // row y - 1
+            uint32_t all = 0xffffffffu;
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                const uint32_t c = __ldg(r + q * bv.pitch), l = __ldg(r + q * bv.pitch - 1),
+                               g = __ldg(r + q * bv.pitch + 1);
+                all &= c & ((c << 1) | (l >> 31)) & ((c >> 1) | (g << 31));
+            }
+            // foreground with a background 8-neighbour, inside the box columns
+            uint32_t cand = __ldg(r + bv.pitch) & ~all;
+            if (bx0 > xw) cand &= ~0u << min(bx0 - xw, 31);
+            if (bx1 < xw + 31) cand &= ~0u >> (xw + 31 - bx1);
+            if (rmask) {
+                uint32_t keep = 0;
+                for (uint32_t m = cand; m; m &= m - 1) {
+                    const int bit = __ffs(m) - 1;
+                    if (cp_hash(xw + bit, y, rmask)) keep |= 1u << bit;
+                }
+                cand = keep;
+            }
+            return cand;
+        };
+        // visit states of a candidate pixel: direction b foreground, b+1 background.  Pixels of
+        // other components inside the box are dropped: their borders may leave the box, where
+        // nothing is a checkpoint, and following them would take arbitrarily long.
+        const int root = first + 1;
+        auto visit_states = [&](int x, int y) -> unsigned {
+            if (lab[(size_t)y * LP + x] != root) return 0u;
+            const unsigned nb = bv.nb(x, y);
+            unsigned starts = nb & ~((nb >> 1) | (nb << 7)) & 0xffu;
+            if (x == xs && y == ys) starts &= ~(1u << b0); // that one is checkpoint 0
+            return starts;
+        };
         while (true) {
             for (int i = tid; i < TRACE_HT; i += TRACE_THREADS) ht_keys[i] = 0;
-            if (tid == 0) {
-                sh_ncp = 1;
-                cp_state[0] = ((ys - by0) << 15) | ((xs - bx0) << 3) | b0;
+            // ---- A: candidate pixels ------------------------------------------------------
+            int mine = 0;
+            for (int i = tid; i < wpr * bh; i += TRACE_THREADS) {
+                int y, xw;
+                mine += __popc(word_cands(i, y, xw));
             }
-            __syncthreads();
-            if (tid == 0) ht_insert(ht_keys, ht_vals, cp_key(xs - bx0, ys - by0, b0), 0);
-            for (int i = tid; i < bw * bh; i += TRACE_THREADS) {
-                const int ly = i / bw, lx = i - ly * bw;
-                const int x = bx0 + lx, y = by0 + ly;
-                if (!cp_hash(x, y, rmask)) continue;
-                // is the pixel part of the component?
-                const int bx = lx + 1;
-                if (!((bits[(size_t)(ly + 1) * row_words + (bx >> 5)] >> (bx & 31)) & 1u)) continue;
-                const unsigned nb = bv.nb(x, y);
-                // visit states: direction b foreground, b+1 background
-                unsigned starts = nb & ~((nb >> 1) | (nb << 7)) & 0xffu;
-                while (starts) {
-                    const int b = __ffs(starts) - 1;
-                    starts &= starts - 1;
-                    if (x == xs && y == ys && b == b0) continue; // already checkpoint 0
-                    const int id = atomicAdd(&sh_ncp, 1);
-                    if (id < TRACE_MAX_CP) {
-                        cp_state[id] = (ly << 15) | (lx << 3) | b;
-                        ht_insert(ht_keys, ht_vals, cp_key(lx, ly, b), id);
+            int ncand;
+            int slot = block_scan(mine, ncand);
+            bool retry = ncand > CAND_CAP;
+            int nstates = 0;
+            if (!retry) {
+                for (int i = tid; i < wpr * bh; i += TRACE_THREADS) {
+                    int y, xw;
+                    for (uint32_t m = word_cands(i, y, xw); m; m &= m - 1)
+                        cand_list[slot++] = (y << 16) | (xw + __ffs(m) - 1);
+                }
+                __syncthreads();
+                // ---- B: states per candidate ----------------------------------------------
+                mine = 0;
+                for (int k = tid; k < ncand; k += TRACE_THREADS)
+                    mine += __popc(visit_states(cand_list[k] & 0xffff, cand_list[k] >> 16));
+                slot = 1 + block_scan(mine, nstates);
+                retry = nstates + 1 > TRACE_MAX_CP;
+            }
+            if (!retry) {
+                // ---- C: fill -------------------------------------------------------------------
+                if (tid == 0) {
+                    sh_ncp = nstates + 1;
+                    cp_state[0] = (ys << 16) | (xs << 3) | b0;
+                    ht_insert(ht_keys, ht_vals, cp_key(xs, ys, b0), 0);
+                }
+                for (int k = tid; k < ncand; k += TRACE_THREADS) {
+                    const int x = cand_list[k] & 0xffff, y = cand_list[k] >> 16;
+                    for (unsigned st = visit_states(x, y); st; st &= st - 1) {
+                        const int b = __ffs(st) - 1;
+                        cp_state[slot] = (y << 16) | (x << 3) | b;
+                        ht_insert(ht_keys, ht_vals, cp_key(x, y, b), slot);
+                        slot++;
                     }
                 }
+                __syncthreads();
+                break;
             }
-            __syncthreads();
-            if (sh_ncp <= TRACE_MAX_CP) break;
             rmask = (rmask << 1) | 1u; // too many: halve the density and start over
             __syncthreads();
         }
         const int ncp = sh_ncp;
+        DBG_T(1);
 
         // ---- pass 1: every checkpoint follows the border to the next checkpoint -------------------
-        const int max_steps = 4 * bw * bh + 16;
+        const int max_steps = 4 * (bw + 2) * (bh + 2) + 16;
         for (int i = tid; i < ncp; i += TRACE_THREADS) {
             const int st = cp_state[i];
-            Segment S;
-            trace_segment<false>(bv, bx0 + ((st >> 3) & 4095), by0 + (st >> 15), st & 7, rmask, ht_keys,
-                                 ht_vals, S, nullptr, max_steps);
-            seg[i] = S;
-            cp_off[i] = -1;
+            int len;
+            SegSums S;
+            const int nx = trace_segment<false>(bv, (st >> 3) & 8191, st >> 16, st & 7, xs, ys, rmask,
+                                                ht_keys, ht_vals, len, S, nullptr, max_steps);
+            seg_a00[i] = S.a00;
+            seg_len[i] = len;
+            dA[i] = (unsigned)len;
+            nxtA[i] = nx == 0 ? -1 : (nx < 0 ? i : nx); // -1 = end of the list (back at the start)
         }
         __syncthreads();
+        DBG_T(2);
 
-        // ---- link the segments of the outer border, starting from the start state -----------------
-        if (tid == 0) {
-            int id = 0, off = 0, guard = 0;
-            long long a00 = 0, a10 = 0, a01 = 0;
-            do {
-                cp_off[id] = off;
-                off += seg[id].len;
-                a00 += seg[id].a00; a10 += seg[id].a10; a01 += seg[id].a01;
-                id = seg[id].next;
-            } while (id > 0 && ++guard < ncp);
-            int keep = -1, base = 0;
-            if (id != 0) atomicOr(&fi->overflow, 8); // border did not close: internal error
-            if (id == 0 && fabs((double)a00) * 0.5 >= area_min) {
-                keep = atomicAdd(&fi->n_kept, 1);
-                base = atomicAdd(&fi->n_points, off);
-                if (keep >= max_kept) { atomicOr(&fi->overflow, 2); keep = -1; }
-                else {
-                    int npts = off;
-                    if (base + off > max_points) { atomicOr(&fi->overflow, 4); npts = 0; }
-                    gofpid_blob *kb = kept + (size_t)z * max_kept + keep;
-                    kb->first = ys * W + xs;
-                    kb->x0 = bx0; kb->y0 = by0; kb->x1 = bx1; kb->y1 = by1;
-                    kb->area_px = cr[CR_AREA];
-                    kb->n_points = npts; kb->point_offset = base;
-                    kb->a00 = a00; kb->a10 = a10; kb->a01 = a01;
-                    if (npts == 0) keep = -1;
+        // ---- rank the segments along the cycle by pointer jumping -----------------------------------
+        {
+            int *na = nxtA, *nbuf = nxtB;
+            unsigned *da = dA, *db = dB;
+            for (int span = 1; span < ncp; span <<= 1) {
+                for (int i = tid; i < ncp; i += TRACE_THREADS) {
+                    const int n = na[i];
+                    if (n >= 0) { db[i] = da[i] + da[n]; nbuf[i] = na[n]; }
+                    else { db[i] = da[i]; nbuf[i] = n; }
+                }
+                __syncthreads();
+                int *t = na; na = nbuf; nbuf = t;
+                unsigned *u = da; da = db; db = u;
+#ifdef GOFPID_TRACE_DEBUG
+                if (span == 1) { DBG_T(7); }
+#endif
+            }
+            DBG_T(6);
+            // na[i] == -1: segment i is on the outer border; da[i] = points from i to the end
+            const unsigned totalN = da[0];
+            const bool closed = na[0] == -1;
+            long long a00 = 0;
+            for (int i = tid; i < ncp; i += TRACE_THREADS) {
+                if (closed && na[i] == -1) {
+                    a00 += seg_a00[i];
+                    nbuf[i] = (int)(totalN - da[i]); // output offset of the segment
+                } else nbuf[i] = -1;
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) a00 += __shfl_xor_sync(0xffffffffu, a00, o);
+            if ((tid & 31) == 0) sh_part[0][tid >> 5] = a00;
+            __syncthreads();
+            DBG_T(3);
+            if (tid == 0) {
+                long long t00 = 0;
+                for (int q = 0; q < TRACE_THREADS / 32; q++) t00 += sh_part[0][q];
+                int keep = -1, base = 0;
+                if (!closed) atomicOr(&fi->overflow, 8); // border did not close: internal error
+                if (closed && fabs((double)t00) * 0.5 >= area_min) {
+                    keep = atomicAdd(&fi->n_kept, 1);
+                    base = atomicAdd(&fi->n_points, (int)totalN);
+                    if (keep >= max_kept) { atomicOr(&fi->overflow, 2); keep = -1; }
+                    else {
+                        int npts = (int)totalN;
+                        if (base + npts > max_points) { atomicOr(&fi->overflow, 4); npts = 0; }
+                        gofpid_blob *kb = kept + (size_t)z * max_kept + keep;
+                        kb->first = ys * W + xs;
+                        kb->x0 = bx0; kb->y0 = by0; kb->x1 = bx1; kb->y1 = by1;
+                        kb->area_px = cr[CR_AREA];
+                        kb->n_points = npts; kb->point_offset = base;
+                        kb->a00 = t00; kb->a10 = 0; kb->a01 = 0;
+                        if (npts == 0) keep = -1;
+                    }
+                }
+                sh_keep = keep; sh_off = base;
+            }
+            __syncthreads();
+            DBG_T(4);
+
+            // ---- pass 2: write the contour, one thread per ranked segment; the first moments are
+            // accumulated on the way (every thread takes part in the reduction)
+            if (sh_keep >= 0) {
+                int32_t *dst = points + ((size_t)z * max_points + sh_off) * 2;
+                long long a10 = 0, a01 = 0;
+                for (int i = tid; i < ncp; i += TRACE_THREADS) {
+                    if (nbuf[i] < 0) continue;
+                    const int st = cp_state[i];
+                    int len;
+                    SegSums S;
+                    trace_segment<true>(bv, (st >> 3) & 8191, st >> 16, st & 7, xs, ys, rmask, ht_keys,
+                                        ht_vals, len, S, dst + 2 * (size_t)nbuf[i], max_steps);
+                    a10 += S.a10; a01 += S.a01;
+                }
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    a10 += __shfl_xor_sync(0xffffffffu, a10, o);
+                    a01 += __shfl_xor_sync(0xffffffffu, a01, o);
+                }
+                if ((tid & 31) == 0) { sh_part[1][tid >> 5] = a10; sh_part[2][tid >> 5] = a01; }
+                __syncthreads();
+                if (tid == 0) {
+                    long long t10 = 0, t01 = 0;
+                    for (int q = 0; q < TRACE_THREADS / 32; q++) { t10 += sh_part[1][q]; t01 += sh_part[2][q]; }
+                    gofpid_blob *kb = kept + (size_t)z * max_kept + sh_keep;
+                    kb->a10 = t10; kb->a01 = t01;
                 }
             }
-            sh_keep = keep; sh_off = base;
         }
+#ifdef GOFPID_TRACE_DEBUG
         __syncthreads();
-
-        // ---- pass 2: write the contour, one thread per linked segment -----------------------------
-        if (sh_keep >= 0) {
-            int32_t *dst = points + ((size_t)z * max_points + sh_off) * 2;
-            for (int i = tid; i < ncp; i += TRACE_THREADS) {
-                if (cp_off[i] < 0) continue;
-                const int st = cp_state[i];
-                Segment S;
-                trace_segment<true>(bv, bx0 + ((st >> 3) & 4095), by0 + (st >> 15), st & 7, rmask, ht_keys,
-                                    ht_vals, S, dst + 2 * (size_t)cp_off[i], max_steps);
+        DBG_T(5);
+        if (tid == 0) {
+            const int k = atomicAdd(&g_trace_dbg_n, 1);
+            if (k < 64) {
+                long long *d = g_trace_dbg + k * 16;
+                d[0] = ci; d[1] = bw; d[2] = bh; d[3] = ncp; d[4] = rmask; d[5] = sh_keep;
+                for (int q = 0; q < 5; q++) d[6 + q] = dbg_t[q + 1] - dbg_t[q];
+                d[11] = blockIdx.x; d[12] = dbg_t[6] - dbg_t[2]; d[13] = dbg_t[7] - dbg_t[2];
             }
         }
+#endif
     }
 }
+
+#ifdef GOFPID_TRACE_DEBUG
+extern "C" __attribute__((visibility("default"))) int gofpid_debug_trace_dump(long long *out)
+{
+    int n = 0;
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(&n, g_trace_dbg_n, sizeof(int));
+    cudaMemcpyFromSymbol(out, g_trace_dbg, sizeof(long long) * 64 * 16);
+    int z = 0;
+    cudaMemcpyToSymbol(g_trace_dbg_n, &z, sizeof(int));
+    return n;
+}
+#endif
 
 // ------------------------------------------------------------------------------------
 // launchers
@@ -710,17 +815,18 @@ int launch_blobs(const BlobBuffers &B, ImageU8 mask, int H, int W, int n_streams
                                 B.info, tick, s));
     const dim3 pgrid((W + 127) / 128, (H + 7) / 8, n_streams);
     flatten_kernel<<<pgrid, dim3(32, 8), 0, s>>>(mask, B.labels, B.labels_pitch, B.labels_stream,
-                                                 B.slot, B.comp, B.info, B.max_blobs, H, W);
+                                                 B.slot, B.comp, B.info, B.max_blobs, B.bitimg,
+                                                 B.bit_pitch, B.bit_stream, H, W);
     GOFPID_CUDA_TRY(cudaGetLastError());
     stats_kernel<<<pgrid, dim3(32, 8), 0, s>>>(mask, B.labels, B.labels_pitch, B.labels_stream,
                                                B.slot, B.comp, B.max_blobs, H, W);
     GOFPID_CUDA_TRY(cudaGetLastError());
     GOFPID_CUDA_TRY(cudaFuncSetAttribute(trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)TRACE_SMEM_BYTES));
-    const dim3 cgrid(n_streams >= 32 ? 8 : (n_streams >= 4 ? 32 : 128), n_streams);
+    const dim3 cgrid(n_streams >= 64 ? 8 : (n_streams >= 8 ? 32 : 148), n_streams);
     trace_kernel<<<cgrid, TRACE_THREADS, TRACE_SMEM_BYTES, s>>>(
         B.labels, B.labels_pitch, B.labels_stream, B.comp, B.info, B.kept, B.points, B.max_blobs,
-        B.max_kept, B.max_points, B.area_min, H, W);
+        B.max_kept, B.max_points, B.area_min, B.bitimg, B.bit_pitch, B.bit_stream, H, W);
     GOFPID_CUDA_TRY(cudaGetLastError());
     if (n_launches) *n_launches = 5;
     return GOFPID_OK;

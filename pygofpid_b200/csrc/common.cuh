@@ -87,6 +87,9 @@ struct FrameTick {
     uint64_t knn_rng;          // RNG state after this frame's fills (all streams)
     // FD
     int32_t fd_valid; // a previous frame exists
+    // where this step's frames are (set by the tick kernel, the only node of the captured
+    // step graph whose parameters change from frame to frame)
+    FrameSrc src;
 };
 
 // ------------------------------------------------------------------ detector state
@@ -128,9 +131,20 @@ struct DetectLaunch {
     const FrameTick *tick;
     cudaStream_t stream;
 };
-int launch_tick(FrameTick *tick, int detector, const Mog2Params &mp, const KnnParams &kp,
-                const int32_t *knn_u_table, int knn_table_len, const uint64_t *pow2tab, int H,
-                int W, int n_streams, cudaStream_t s);
+struct TickArgs { // by-value kernel arguments of tick_kernel, kept by the pipeline for graph updates
+    FrameTick *tick;
+    int detector;
+    Mog2Params mp;
+    KnnParams kp;
+    const int32_t *knn_u_table;
+    int knn_table_len;
+    const uint64_t *pow2tab;
+    int total, n_streams;
+    FrameSrc src;
+};
+int launch_tick(const TickArgs &a, cudaStream_t s);
+const void *tick_kernel_func();
+void tick_kernel_params(TickArgs &a, void **params); // params[10]
 int launch_blur_only(const DetectLaunch &L, ImageU8 dst);
 int launch_fd(const DetectLaunch &L, FdModel model, int thr);
 int launch_mog2(const DetectLaunch &L, Mog2Model model, const Mog2Params &mp);
@@ -166,6 +180,9 @@ struct BlobBuffers {
     size_t labels_pitch;  // elements
     size_t labels_stream; // elements between streams
     int32_t *slot;        // per stream: LP*H int32, component slot of root pixels (sparse)
+    uint32_t *bitimg;     // per stream: (H+2) rows of bit_pitch words; pixel (x,y) = bit x+32 of row y+1
+    int bit_pitch;        // words per row (>= W/32 + 2 guard words)
+    size_t bit_stream;    // words between streams
     int32_t *comp;        // per stream: max_blobs * 8 int32 component records
     gofpid_frame_info *info; // per stream
     int32_t *cand;        // per stream: max_blobs candidate slots

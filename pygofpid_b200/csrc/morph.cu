@@ -92,7 +92,7 @@ int morph_plan_create(const gofpid_morph_op *ops, int n_ops, MorphPlan *plan)
     const int hl4 = (plan->halo_l + 3) & ~3, hr4 = (plan->halo_r + 3) & ~3;
     const int stride = MORPH_SLACK + hl4 + plan->tile_w + hr4 + MORPH_SLACK;
     const int rows = plan->tile_h + plan->halo_t + plan->halo_b;
-    plan->smem_bytes = (size_t)3 * rows * stride;
+    plan->smem_bytes = (size_t)6 * rows * stride; // three images, each split in two u16x2 planes
     return GOFPID_OK;
 }
 
@@ -105,91 +105,167 @@ void morph_plan_destroy(MorphPlan *plan)
 // ------------------------------------------------------------------------------------
 // device helpers
 // ------------------------------------------------------------------------------------
-struct Pair { uint32_t e, o; }; // even bytes (0,2) and odd bytes (1,3) of a word as u16x2
+// Shared-memory images are kept SPLIT: a word of four pixels p0..p3 is stored as
+// E = (p0, p2) and O = (p1, p3), two u16 lanes each, in two planes.  Packed VIMNMX (u16x2,
+// three inputs) then works on loaded words directly, and a horizontal shift by one pixel is a
+// swap of planes plus a 16-bit funnel shift.
+__device__ __forceinline__ uint32_t split_e(uint32_t w) { return __byte_perm(w, 0, 0x4240); }
+__device__ __forceinline__ uint32_t split_o(uint32_t w) { return __byte_perm(w, 0, 0x4341); }
+__device__ __forceinline__ uint32_t join_eo(uint32_t e, uint32_t o) { return e | (o << 8); }
 
-__device__ __forceinline__ Pair split(uint32_t w)
+template <bool DIL> __device__ __forceinline__ uint32_t mm2(uint32_t a, uint32_t b)
 {
-    Pair p;
-    p.e = __byte_perm(w, 0, 0x4240);
-    p.o = __byte_perm(w, 0, 0x4341);
-    return p;
+    return DIL ? __vmaxu2(a, b) : __vminu2(a, b);
 }
-template <bool DIL>
-__device__ __forceinline__ void acc(Pair &a, uint32_t w)
+template <bool DIL> __device__ __forceinline__ uint32_t mm3(uint32_t a, uint32_t b, uint32_t c)
 {
-    const Pair p = split(w);
-    if (DIL) { a.e = __vmaxu2(a.e, p.e); a.o = __vmaxu2(a.o, p.o); }
-    else { a.e = __vminu2(a.e, p.e); a.o = __vminu2(a.o, p.o); }
+    return DIL ? __vimax3_u16x2(a, b, c) : __vimin3_u16x2(a, b, c);
 }
-__device__ __forceinline__ uint32_t join(const Pair &a) { return a.e | (a.o << 8); }
+// 32 bits of a u16 stream starting at u16 index p (words lo = plane[p>>1], hi = plane[(p>>1)+1])
+__device__ __forceinline__ uint32_t win16(uint32_t lo, uint32_t hi, int p)
+{
+    return __funnelshift_r(lo, hi, (p & 1) << 4);
+}
 
-// min/max over `len` consecutive byte-shifted words starting at byte column `start`
-template <bool DIL>
-__device__ __forceinline__ void window(Pair &a, const uint32_t *row, int start, int len,
-                                       int nwords)
+struct Planes {
+    uint32_t *e, *o; // [rows][nwords]
+};
+
+// Row pass of a K-wide full rectangle (anchor K/2) for output word wc, taps known at compile time.
+//   E_out(t) = even t: Ewin(t/2)      odd t: Owin((t-1)/2)
+//   O_out(t) = even t: Owin(t/2)      odd t: Ewin((t+1)/2)      (win index relative to 2*wc)
+template <bool DIL, int K>
+__device__ __forceinline__ void row_rect(const uint32_t *er, const uint32_t *orow, int wc, int nwords,
+                                         uint32_t &oute, uint32_t &outo)
 {
-    int wi = start >> 2, sh = start & 3;
-    uint32_t lo = row[min(max(wi, 0), nwords - 1)];
-    uint32_t hi = row[min(max(wi + 1, 0), nwords - 1)];
+    constexpr int R = K / 2;
+    static_assert(K % 2 == 1 && R <= 3, "specialised for 3, 5, 7");
+    const int wm = max(wc - 1, 0), wp = min(wc + 1, nwords - 1);
+    const uint32_t e[3] = {er[wm], er[wc], er[wp]}, o[3] = {orow[wm], orow[wc], orow[wp]};
+    // windows at u16 offsets -2..+2 relative to the word: index i -> array slot i + 2
+    uint32_t ew[5], ow[5];
+    ew[0] = e[0]; ew[2] = e[1]; ew[4] = e[2];
+    ow[0] = o[0]; ow[2] = o[1]; ow[4] = o[2];
+    ew[1] = __funnelshift_r(e[0], e[1], 16); ew[3] = __funnelshift_r(e[1], e[2], 16);
+    ow[1] = __funnelshift_r(o[0], o[1], 16); ow[3] = __funnelshift_r(o[1], o[2], 16);
+    uint32_t ae = DIL ? 0u : 0x00ff00ffu, ao = ae;
+#pragma unroll
+    for (int t = -R; t <= R; t++) {
+        if ((t & 1) == 0) {
+            ae = mm2<DIL>(ae, ew[t / 2 + 2]);
+            ao = mm2<DIL>(ao, ow[t / 2 + 2]);
+        } else {
+            ae = mm2<DIL>(ae, ow[(t - 1) / 2 + 2]);
+            ao = mm2<DIL>(ao, ew[(t + 1) / 2 + 2]);
+        }
+    }
+    oute = ae; outo = ao;
+}
+
+// Generic horizontal window: min/max over `len` taps starting at pixel offset t0 (relative to
+// the first pixel of word wc), any length / anchor.
+template <bool DIL>
+__device__ __forceinline__ void window_split(uint32_t &ae, uint32_t &ao, const uint32_t *er,
+                                             const uint32_t *orow, int wc, int t0, int len, int nwords)
+{
+    int p = 2 * wc + (t0 >> 1); // u16 stream index (floor division also for negative t0)
+    int parity = t0 & 1;
+    int wi = p >> 1;
+    auto ld = [&](const uint32_t *pl, int i) { return pl[min(max(i, 0), nwords - 1)]; };
+    uint32_t e_lo = ld(er, wi), e_hi = ld(er, wi + 1), o_lo = ld(orow, wi), o_hi = ld(orow, wi + 1);
     for (int j = 0; j < len; j++) {
-        acc<DIL>(a, __funnelshift_r(lo, hi, 8 * sh));
-        if (++sh == 4) {
-            sh = 0; wi++;
-            lo = hi;
-            hi = row[min(max(wi + 1, 0), nwords - 1)];
+        if (parity == 0) {
+            ae = mm2<DIL>(ae, win16(e_lo, e_hi, p));
+            ao = mm2<DIL>(ao, win16(o_lo, o_hi, p));
+            parity = 1;
+        } else {
+            ae = mm2<DIL>(ae, win16(o_lo, o_hi, p));
+            p++;
+            if ((p >> 1) != wi) {
+                wi = p >> 1;
+                e_lo = e_hi; o_lo = o_hi;
+                e_hi = ld(er, wi + 1); o_hi = ld(orow, wi + 1);
+            }
+            ao = mm2<DIL>(ao, win16(e_lo, e_hi, p));
+            parity = 0;
         }
     }
 }
+
+struct OpGeom {
+    int r0, r1, w0, nw;     // valid output rows [r0, r1) and word columns [w0, w0 + nw)
+    int gy0, gx0, H, W;     // image coordinates of buffer (0, 0)
+    int nwords, rows;
+};
 
 template <bool DIL>
 __device__ __forceinline__ void run_op(const MorphOpDev &op, const MorphRun *__restrict__ runs,
-                                       const uint8_t *A, uint8_t *T, uint8_t *B, int stride,
-                                       int r0, int r1, int c0, int c1, // valid output region
-                                       int gy0, int gx0,               // image coords of (0,0)
-                                       int H, int W, uint32_t ident_next)
+                                       Planes A, Planes T, Planes B, const OpGeom &G,
+                                       uint32_t ident_next)
 {
     const int tid = threadIdx.x;
-    const int nwords = stride >> 2;
-    const int w0 = c0 >> 2, w1 = (c1 + 3) >> 2; // word columns covering the valid region
-    const int nw = w1 - w0;
-    const Pair init = DIL ? Pair{0u, 0u} : Pair{0x00ff00ffu, 0x00ff00ffu};
+    const int nwords = G.nwords;
+    const uint32_t init = DIL ? 0u : 0x00ff00ffu;
+    // one division per step and thread: column c and first row r of this thread
+    const int c = tid % G.nw, rofs = tid / G.nw, rstep = MORPH_THREADS / G.nw;
+    const int wc = G.w0 + c;
+    const bool active = rofs < rstep;
+    // in-image lanes of this word column (E = pixels 0, 2; O = pixels 1, 3)
+    const int gx = G.gx0 + wc * 4;
+    const uint32_t inE = ((gx >= 0 && gx < G.W) ? 0x0000ffffu : 0u) | ((gx + 2 >= 0 && gx + 2 < G.W) ? 0xffff0000u : 0u);
+    const uint32_t inO = ((gx + 1 >= 0 && gx + 1 < G.W) ? 0x0000ffffu : 0u) | ((gx + 3 >= 0 && gx + 3 < G.W) ? 0xffff0000u : 0u);
+    const uint32_t idn = ident_next & 0x00ff00ffu;
+    const bool fast_rect = op.is_rect && op.kw == op.kh && (op.kw == 3 || op.kw == 5 || op.kw == 7);
 
     if (op.is_rect) {
         // row pass over the rows the column pass will read
-        const int rr0 = r0 - op.ay, rr1 = r1 + (op.kh - 1 - op.ay);
-        for (int i = tid; i < (rr1 - rr0) * nw; i += MORPH_THREADS) {
-            const int r = rr0 + i / nw, wc = w0 + i % nw;
-            Pair a = init;
-            window<DIL>(a, reinterpret_cast<const uint32_t *>(A + (size_t)r * stride),
-                        wc * 4 - op.ax, op.kw, nwords);
-            reinterpret_cast<uint32_t *>(T + (size_t)r * stride)[wc] = join(a);
+        const int rr0 = G.r0 - op.ay, rr1 = G.r1 + (op.kh - 1 - op.ay);
+        if (active) {
+            for (int r = rr0 + rofs; r < rr1; r += rstep) {
+                const uint32_t *er = A.e + (size_t)r * nwords, *orow = A.o + (size_t)r * nwords;
+                uint32_t ae = init, ao = init;
+                if (fast_rect && op.kw == 5) row_rect<DIL, 5>(er, orow, wc, nwords, ae, ao);
+                else if (fast_rect && op.kw == 3) row_rect<DIL, 3>(er, orow, wc, nwords, ae, ao);
+                else if (fast_rect) row_rect<DIL, 7>(er, orow, wc, nwords, ae, ao);
+                else window_split<DIL>(ae, ao, er, orow, wc, -op.ax, op.kw, nwords);
+                T.e[(size_t)r * nwords + wc] = ae;
+                T.o[(size_t)r * nwords + wc] = ao;
+            }
         }
         __syncthreads();
     }
-    for (int i = tid; i < (r1 - r0) * nw; i += MORPH_THREADS) {
-        const int r = r0 + i / nw, wc = w0 + i % nw;
-        Pair a = init;
-        if (op.is_rect) {
-            for (int k = 0; k < op.kh; k++)
-                acc<DIL>(a, reinterpret_cast<const uint32_t *>(T + (size_t)(r + k - op.ay) * stride)[wc]);
-        } else {
-            for (int q = op.run_begin; q < op.run_end; q++) {
-                const MorphRun run = runs[q];
-                window<DIL>(a, reinterpret_cast<const uint32_t *>(A + (size_t)(r + run.dy) * stride),
-                            wc * 4 + run.dx, run.len, nwords);
+    if (active) {
+        for (int r = G.r0 + rofs; r < G.r1; r += rstep) {
+            uint32_t ae = init, ao = init;
+            if (op.is_rect) {
+                const uint32_t *te = T.e + (size_t)(r - op.ay) * nwords + wc;
+                const uint32_t *to = T.o + (size_t)(r - op.ay) * nwords + wc;
+                if (fast_rect && op.kh == 5) {
+                    ae = mm3<DIL>(mm3<DIL>(te[0], te[nwords], te[2 * nwords]), te[3 * nwords], te[4 * nwords]);
+                    ao = mm3<DIL>(mm3<DIL>(to[0], to[nwords], to[2 * nwords]), to[3 * nwords], to[4 * nwords]);
+                } else if (fast_rect && op.kh == 3) {
+                    ae = mm3<DIL>(te[0], te[nwords], te[2 * nwords]);
+                    ao = mm3<DIL>(to[0], to[nwords], to[2 * nwords]);
+                } else {
+                    for (int k = 0; k < op.kh; k++) {
+                        ae = mm2<DIL>(ae, te[(size_t)k * nwords]);
+                        ao = mm2<DIL>(ao, to[(size_t)k * nwords]);
+                    }
+                }
+            } else {
+                for (int q = op.run_begin; q < op.run_end; q++) {
+                    const MorphRun run = runs[q];
+                    window_split<DIL>(ae, ao, A.e + (size_t)(r + run.dy) * nwords,
+                                      A.o + (size_t)(r + run.dy) * nwords, wc, run.dx, run.len, nwords);
+                }
             }
+            // cells outside the image take the identity of the NEXT step (OpenCV ignores them)
+            const int gy = G.gy0 + r;
+            const bool rin = gy >= 0 && gy < G.H;
+            const uint32_t me = rin ? inE : 0u, mo = rin ? inO : 0u;
+            B.e[(size_t)r * nwords + wc] = (ae & me) | (idn & ~me);
+            B.o[(size_t)r * nwords + wc] = (ao & mo) | (idn & ~mo);
         }
-        // cells outside the image take the identity of the NEXT step (OpenCV ignores them)
-        uint32_t res = join(a);
-        const int gy = gy0 + r, gx = gx0 + wc * 4;
-        uint32_t inmask = 0;
-        if (gy >= 0 && gy < H) {
-#pragma unroll
-            for (int b = 0; b < 4; b++)
-                if (gx + b >= 0 && gx + b < W) inmask |= 0xffu << (8 * b);
-        }
-        res = (res & inmask) | (ident_next & ~inmask);
-        reinterpret_cast<uint32_t *>(B + (size_t)r * stride)[wc] = res;
     }
     __syncthreads();
 }
@@ -200,19 +276,24 @@ morph_chain_kernel(MorphPlan plan, ImageU8 src, ImageU8 dst, int H, int W)
     extern __shared__ __align__(16) unsigned char smem[];
     const int tid = threadIdx.x;
     const int hl4 = (plan.halo_l + 3) & ~3, hr4 = (plan.halo_r + 3) & ~3;
-    const int stride = MORPH_SLACK + hl4 + plan.tile_w + hr4 + MORPH_SLACK;
+    const int stride = MORPH_SLACK + hl4 + plan.tile_w + hr4 + MORPH_SLACK; // pixels per staged row
     const int rows = plan.tile_h + plan.halo_t + plan.halo_b;
     const int nwords = stride >> 2;
-    uint8_t *A = smem, *T = smem + (size_t)rows * stride, *B = smem + (size_t)2 * rows * stride;
+    const size_t plane = (size_t)rows * nwords;
+    uint32_t *base = reinterpret_cast<uint32_t *>(smem);
+    Planes A{base, base + plane}, T{base + 2 * plane, base + 3 * plane}, B{base + 4 * plane, base + 5 * plane};
 
     const int x0 = blockIdx.x * plan.tile_w, y0 = blockIdx.y * plan.tile_h;
     const int gx0 = x0 - hl4 - MORPH_SLACK; // image x of buffer column 0 (multiple of 4)
     const int gy0 = y0 - plan.halo_t;
     const uint8_t *sbase = src.base + (size_t)blockIdx.z * src.stream_stride;
+    uint8_t *dbase = dst.base + (size_t)blockIdx.z * dst.stream_stride;
     const bool aligned = ((reinterpret_cast<uintptr_t>(sbase) | src.pitch) & 3) == 0;
+    const bool daligned = ((reinterpret_cast<uintptr_t>(dbase) | dst.pitch) & 3) == 0;
     const uint32_t ident0 = plan.n_ops && plan.ops[0].op == GOFPID_MORPH_ERODE ? 0xffffffffu : 0u;
 
     // ---- stage the tile + halo; out-of-image cells get the first step's identity --------
+    bool any_set = false, any_clear = false; // over in-image bytes: some != 0, some != 255
     for (int i = tid; i < rows * nwords; i += MORPH_THREADS) {
         const int r = i / nwords, wc = i - r * nwords;
         const int gy = gy0 + r, gx = gx0 + wc * 4;
@@ -221,44 +302,68 @@ morph_chain_kernel(MorphPlan plan, ImageU8 src, ImageU8 dst, int H, int W)
             const uint8_t *row = sbase + (size_t)gy * src.pitch;
             if (aligned && gx >= 0 && gx + 3 < W) {
                 v = *reinterpret_cast<const uint32_t *>(row + gx);
+                any_set |= v != 0u; any_clear |= v != 0xffffffffu;
             } else {
 #pragma unroll
                 for (int b = 0; b < 4; b++)
-                    if (gx + b >= 0 && gx + b < W)
-                        v = (v & ~(0xffu << (8 * b))) | ((uint32_t)row[gx + b] << (8 * b));
+                    if (gx + b >= 0 && gx + b < W) {
+                        const uint32_t px = row[gx + b];
+                        v = (v & ~(0xffu << (8 * b))) | (px << (8 * b));
+                        any_set |= px != 0u; any_clear |= px != 255u;
+                    }
             }
         }
-        reinterpret_cast<uint32_t *>(A + (size_t)r * stride)[wc] = v;
+        A.e[i] = split_e(v);
+        A.o[i] = split_o(v);
     }
-    __syncthreads();
+    // (__syncthreads_or returns a truth value, not the OR of the arguments: one call per flag)
+    const int uniform = (__syncthreads_or(any_set) ? 1 : 0) | (__syncthreads_or(any_clear) ? 2 : 0);
+
+    const int tw4 = plan.tile_w >> 2;
+    const int cbase = (MORPH_SLACK + hl4) >> 2; // buffer word column of x0
+    if (plan.n_ops > 0 && uniform != 3) {
+        // every in-image pixel the tile can see is 0 (or every one is 255): min / max over any
+        // structuring element reproduces that value, so the whole chain is the identity here
+        const uint32_t v = (uniform & 1) ? 0xffffffffu : 0u;
+        for (int i = tid; i < plan.tile_h * tw4; i += MORPH_THREADS) {
+            const int r = i / tw4, wc = i - r * tw4;
+            const int gy = y0 + r, gx = x0 + wc * 4;
+            if (gy >= H || gx >= W) continue;
+            uint8_t *row = dbase + (size_t)gy * dst.pitch;
+            if (daligned && gx + 3 < W) *reinterpret_cast<uint32_t *>(row + gx) = v;
+            else {
+#pragma unroll
+                for (int b = 0; b < 4; b++)
+                    if (gx + b < W) row[gx + b] = (uint8_t)v;
+            }
+        }
+        return;
+    }
 
     // ---- run the chain, shrinking the valid region by each step's extent -----------------
+    OpGeom G;
+    G.gy0 = gy0; G.gx0 = gx0; G.H = H; G.W = W; G.nwords = nwords; G.rows = rows;
     int r0 = 0, r1 = rows, c0 = MORPH_SLACK + hl4 - plan.halo_l,
         c1 = MORPH_SLACK + hl4 + plan.tile_w + plan.halo_r;
     for (int k = 0; k < plan.n_ops; k++) {
         const MorphOpDev &op = plan.ops[k];
         r0 += op.ay; r1 -= op.kh - 1 - op.ay;
         c0 += op.ax; c1 -= op.kw - 1 - op.ax;
+        G.r0 = r0; G.r1 = r1; G.w0 = c0 >> 2; G.nw = ((c1 + 3) >> 2) - G.w0;
         const uint32_t ident_next =
             (k + 1 < plan.n_ops && plan.ops[k + 1].op == GOFPID_MORPH_ERODE) ? 0xffffffffu : 0u;
-        if (op.op == GOFPID_MORPH_DILATE)
-            run_op<true>(op, plan.d_runs, A, T, B, stride, r0, r1, c0, c1, gy0, gx0, H, W, ident_next);
-        else
-            run_op<false>(op, plan.d_runs, A, T, B, stride, r0, r1, c0, c1, gy0, gx0, H, W, ident_next);
-        uint8_t *t = A; A = B; B = t;
+        if (op.op == GOFPID_MORPH_DILATE) run_op<true>(op, plan.d_runs, A, T, B, G, ident_next);
+        else run_op<false>(op, plan.d_runs, A, T, B, G, ident_next);
+        const Planes t = A; A = B; B = t;
     }
 
     // ---- write the tile -----------------------------------------------------------------
-    uint8_t *dbase = dst.base + (size_t)blockIdx.z * dst.stream_stride;
-    const bool daligned = ((reinterpret_cast<uintptr_t>(dbase) | dst.pitch) & 3) == 0;
-    const int tw4 = plan.tile_w >> 2;
-    const int cbase = MORPH_SLACK + hl4; // buffer column of x0
     for (int i = tid; i < plan.tile_h * tw4; i += MORPH_THREADS) {
         const int r = i / tw4, wc = i - r * tw4;
         const int gy = y0 + r, gx = x0 + wc * 4;
         if (gy >= H || gx >= W) continue;
-        const uint32_t v = reinterpret_cast<const uint32_t *>(
-            A + (size_t)(r + plan.halo_t) * stride + cbase)[wc];
+        const size_t si = (size_t)(r + plan.halo_t) * nwords + cbase + wc;
+        const uint32_t v = join_eo(A.e[si], A.o[si]);
         uint8_t *row = dbase + (size_t)gy * dst.pitch;
         if (daligned && gx + 3 < W) {
             *reinterpret_cast<uint32_t *>(row + gx) = v;

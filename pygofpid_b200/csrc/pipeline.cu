@@ -8,6 +8,7 @@
 
 #include <math.h>
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -70,6 +71,15 @@ struct gofpid_pipeline {
     bool profiling = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int launch_count = 0;
+
+    // the step as a CUDA graph: captured once, replayed per frame; only the tick kernel's
+    // arguments (where the frames are) change between launches
+    bool use_graph = true;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t graph_exec = nullptr;
+    cudaGraphNode_t tick_node = nullptr;
+    TickArgs tick_args;
+    int graph_launches = 0;
 };
 
 namespace {
@@ -157,7 +167,7 @@ void free_all(gofpid_pipeline *p)
     cudaFree(p->fd.prev);
     cudaFree(p->d_knn_table); cudaFree(p->d_pow2tab);
     morph_plan_destroy(&p->morph);
-    cudaFree(p->blobs.labels); cudaFree(p->blobs.slot); cudaFree(p->blobs.comp);
+    cudaFree(p->blobs.labels); cudaFree(p->blobs.slot); cudaFree(p->blobs.comp); cudaFree(p->blobs.bitimg);
     cudaFree(p->blobs.info); cudaFree(p->blobs.cand); cudaFree(p->blobs.kept); cudaFree(p->blobs.points);
     cudaFree(p->d_frames);
     if (p->h_frames) cudaFreeHost(p->h_frames);
@@ -165,6 +175,8 @@ void free_all(gofpid_pipeline *p)
     if (p->h_kept) cudaFreeHost(p->h_kept);
     if (p->h_points) cudaFreeHost(p->h_points);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
+    if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
+    if (p->graph) cudaGraphDestroy(p->graph);
     if (p->stream) cudaStreamDestroy(p->stream);
 }
 
@@ -232,6 +244,16 @@ int build(gofpid_pipeline *p)
         return GOFPID_ERR_INVALID;
     }
 
+    p->tick_args.tick = p->d_tick; p->tick_args.detector = cfg.detector;
+    p->tick_args.mp = p->mog2p; p->tick_args.kp = p->knnp;
+    p->tick_args.knn_u_table = p->d_knn_table; p->tick_args.knn_table_len = p->knn_table_len;
+    p->tick_args.pow2tab = p->d_pow2tab; p->tick_args.total = H * W; p->tick_args.n_streams = S;
+    p->tick_args.src = FrameSrc{nullptr, 0, 0};
+    {
+        const char *e = getenv("GOFPID_NO_GRAPH");
+        p->use_graph = !(e && e[0] == '1');
+    }
+
     GOFPID_TRY(morph_plan_create(p->cfg.morph, p->cfg.n_morph, &p->morph));
     p->final_mask = p->cfg.n_morph > 0 ? 1 : 0;
 
@@ -248,6 +270,10 @@ int build(gofpid_pipeline *p)
         if (B.labels_stream >= (size_t)0x7fffffff) { set_error("frame too large for int32 labels"); return GOFPID_ERR_UNSUPPORTED; }
         GOFPID_TRY(alloc_zero((void **)&B.labels, B.labels_stream * sizeof(int32_t) * S));
         GOFPID_TRY(alloc_zero((void **)&B.slot, B.labels_stream * sizeof(int32_t) * S));
+        if (W > 8191 || H > 32767) { set_error("frames beyond 8191 x 32767 are not supported by the border tracer"); return GOFPID_ERR_UNSUPPORTED; }
+        B.bit_pitch = (int)round_up((size_t)(W + 31) / 32 + 2, 4);
+        B.bit_stream = (size_t)B.bit_pitch * (H + 2);
+        GOFPID_TRY(alloc_zero((void **)&B.bitimg, B.bit_stream * sizeof(uint32_t) * S));
         GOFPID_TRY(alloc_zero((void **)&B.comp, (size_t)B.max_blobs * 8 * sizeof(int32_t) * S));
         GOFPID_TRY(alloc_zero((void **)&B.info, sizeof(gofpid_frame_info) * S));
         GOFPID_TRY(alloc_zero((void **)&B.kept, sizeof(gofpid_blob) * B.max_kept * S));
@@ -260,18 +286,17 @@ int build(gofpid_pipeline *p)
     return reset_state(p);
 }
 
-int run_step(gofpid_pipeline *p, const uint8_t *d_frames, size_t pitch, size_t stream_stride,
-             cudaStream_t s)
+// Enqueues the kernels of one step on `s` (also used under stream capture).
+int enqueue_step(gofpid_pipeline *p, const FrameSrc &src, cudaStream_t s, bool prof, int *n_launches)
 {
-    const bool prof = p->profiling;
     int launches = 0;
     if (prof) GOFPID_CUDA_TRY(cudaEventRecord(p->ev[0], s));
-    GOFPID_TRY(launch_tick(p->d_tick, p->cfg.detector, p->mog2p, p->knnp, p->d_knn_table,
-                           p->knn_table_len, p->d_pow2tab, p->H, p->W, p->n_streams, s));
+    p->tick_args.src = src;
+    GOFPID_TRY(launch_tick(p->tick_args, s));
     if (prof) GOFPID_CUDA_TRY(cudaEventRecord(p->ev[4], s));
     DetectLaunch L;
     L.H = p->H; L.W = p->W; L.C = p->C; L.n_streams = p->n_streams;
-    L.src = FrameSrc{d_frames, pitch, stream_stride};
+    L.src = src;
     L.blur = p->blur;
     L.mask = ImageU8{p->d_mask[0], p->mask_pitch, p->mask_stream};
     L.tick = p->d_tick;
@@ -294,6 +319,62 @@ int run_step(gofpid_pipeline *p, const uint8_t *d_frames, size_t pitch, size_t s
         launches += nb;
     }
     if (prof) GOFPID_CUDA_TRY(cudaEventRecord(p->ev[3], s));
+    if (n_launches) *n_launches = launches;
+    return GOFPID_OK;
+}
+
+// Captures the step once (on the pipeline's own stream) and finds the tick kernel's node.
+int build_graph(gofpid_pipeline *p, const FrameSrc &src)
+{
+    // a plain launch first: sets the per-function attributes (dynamic smem opt-in) outside capture
+    int launches = 0;
+    GOFPID_CUDA_TRY(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
+    int rc = enqueue_step(p, src, p->stream, false, &launches);
+    cudaGraph_t g = nullptr;
+    cudaError_t e = cudaStreamEndCapture(p->stream, &g);
+    if (rc != GOFPID_OK) { if (g) cudaGraphDestroy(g); return rc; }
+    if (e != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(e)); return GOFPID_ERR_CUDA; }
+    p->graph = g;
+    size_t n = 0;
+    GOFPID_CUDA_TRY(cudaGraphGetNodes(g, nullptr, &n));
+    std::vector<cudaGraphNode_t> nodes(n);
+    GOFPID_CUDA_TRY(cudaGraphGetNodes(g, nodes.data(), &n));
+    p->tick_node = nullptr;
+    for (size_t i = 0; i < n; i++) {
+        cudaGraphNodeType t;
+        GOFPID_CUDA_TRY(cudaGraphNodeGetType(nodes[i], &t));
+        if (t != cudaGraphNodeTypeKernel) continue;
+        cudaKernelNodeParams kp;
+        GOFPID_CUDA_TRY(cudaGraphKernelNodeGetParams(nodes[i], &kp));
+        if (kp.func == tick_kernel_func()) { p->tick_node = nodes[i]; break; }
+    }
+    if (!p->tick_node) { set_error("graph capture: tick node not found"); return GOFPID_ERR_CUDA; }
+    GOFPID_CUDA_TRY(cudaGraphInstantiate(&p->graph_exec, g, 0));
+    p->graph_launches = launches;
+    return GOFPID_OK;
+}
+
+int run_step(gofpid_pipeline *p, const uint8_t *d_frames, size_t pitch, size_t stream_stride,
+             cudaStream_t s)
+{
+    const FrameSrc src{d_frames, pitch, stream_stride};
+    int launches = 0;
+    if (p->use_graph && !p->profiling && p->stepped) {
+        // (the very first step runs eagerly: it also performs the one-time function setup)
+        if (!p->graph_exec) GOFPID_TRY(build_graph(p, src));
+        p->tick_args.src = src;
+        void *params[10];
+        tick_kernel_params(p->tick_args, params);
+        cudaKernelNodeParams kp = {};
+        kp.func = const_cast<void *>(tick_kernel_func());
+        kp.gridDim = dim3(1); kp.blockDim = dim3(32); kp.sharedMemBytes = 0;
+        kp.kernelParams = params; kp.extra = nullptr;
+        GOFPID_CUDA_TRY(cudaGraphExecKernelNodeSetParams(p->graph_exec, p->tick_node, &kp));
+        GOFPID_CUDA_TRY(cudaGraphLaunch(p->graph_exec, s));
+        launches = p->graph_launches;
+    } else {
+        GOFPID_TRY(enqueue_step(p, src, s, p->profiling, &launches));
+    }
     p->launch_count = launches;
     p->last_stream = s;
     p->results_valid = false;
