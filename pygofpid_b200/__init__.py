@@ -7,5 +7,7 @@ this package is the thin host side.  There is no CPU fallback.
 __version__ = "0.1.0"
 
 from .hotpath import HotPath  # noqa: F401
+from .pipeline import GOFPID  # noqa: F401
+from .segmentation import ForegroundEstimator, FrameDifferencing, ViBe  # noqa: F401
 
-__all__ = ["HotPath", "__version__"]
+__all__ = ["GOFPID", "HotPath", "ForegroundEstimator", "FrameDifferencing", "ViBe", "__version__"]

@@ -1,0 +1,520 @@
+"""`GOFPID`: good-old-fashioned perimeter intrusion detection, drop-in for pygofpid.pipeline.GOFPID.
+
+Same constructor parameters, `initialize()` / `detect(X)` / `display(X, display)` methods,
+`foreground_mask_` / `blobs_` / `tracked_blobs_` / `input_shape_` attributes and the same
+exceptions for the same mistakes as the reference (pygofpid/pipeline.py:168-283, 434-493).
+
+What changed is where the per-frame pixel work runs: steps 1-4 of `detect`
+
+    1. spatial blur            (reference pipeline.py:462-467, cv.GaussianBlur / cv.blur)
+    2. foreground detection    (pipeline.py:470, MOG2 / KNN / frame differencing)
+    3. mask morphology         (pipeline.py:473-476, cv.erode / cv.dilate chain)
+    4. blob creation           (pipeline.py:555-588, findContours + contourArea + moments)
+
+are one CUDA pipeline (`HotPath`, libgofpid_b200.so) whose background model lives in HBM.
+Steps 5-7 (tracking, post-filtering, alarm) consume the blob list on the host exactly as the
+reference does; they touch a handful of blobs per frame and no pixels.
+
+The OpenCV callables of the reference's parameter dicts (`cv.GaussianBlur`, `cv.blur`,
+`cv.erode`, `cv.dilate`) are accepted as they are and mapped to kernel configurations by
+identity / name; their string names work too when OpenCV is not installed.  There is no CPU
+fallback for steps 1-4: anything the kernels do not cover raises NotImplementedError.
+"""
+import numpy as np
+
+from .helpers import (SimpleLinearRegression, normalize_coords, point_in_polygon, read_first_frame,
+                      unnormalize_coords)
+from .segmentation import ViBe
+
+try:  # OpenCV is only needed for the parameter objects users pass in, and for display()
+    import cv2 as cv
+except Exception:  # pragma: no cover
+    cv = None
+
+_BORDER_DEFAULT = 4  # cv.BORDER_DEFAULT == cv.BORDER_REFLECT_101
+_COLOR_BGR2GRAY, _COLOR_RGB2GRAY = 6, 7
+
+
+def _cv_name(fun):
+    """'GaussianBlur' | 'blur' | 'erode' | 'dilate' for a cv2 callable or its name."""
+    if isinstance(fun, str):
+        return fun
+    if cv is not None:
+        for name in ("GaussianBlur", "blur", "erode", "dilate"):
+            if fun is getattr(cv, name, None):
+                return name
+    return getattr(fun, "__name__", None)
+
+
+def _rect_kernel(n):
+    return np.ones((n, n), dtype=np.uint8)
+
+
+def _default_blur():
+    return {'fun': cv.GaussianBlur if cv is not None else 'GaussianBlur', 'ksize': (3, 3),
+            'borderType': _BORDER_DEFAULT}
+
+
+def _default_morph():
+    return [{'fun': cv.erode if cv is not None else 'erode', 'kernel': _rect_kernel(5)},
+            {'fun': cv.dilate if cv is not None else 'dilate', 'kernel': _rect_kernel(5)}]
+
+
+def _to_gray(X, code):
+    """cv.cvtColor(X, COLOR_BGR2GRAY | COLOR_RGB2GRAY) for uint8 (15-bit fixed point, exact)."""
+    w = (3735, 19235, 9798) if code == _COLOR_BGR2GRAY else (9798, 19235, 3735)
+    Xi = X.astype(np.uint32)
+    return ((Xi[..., 0] * w[0] + Xi[..., 1] * w[1] + Xi[..., 2] * w[2] + 16384) >> 15).astype(np.uint8)
+
+
+class GOFPID():
+    """GOFPID: good old fashioned perimeter intrusion detection system (B200 hot path).
+
+    Parameters
+    ----------
+    convert : OpenCV color conversion code | None, default=None
+        Convert the input frame from colour to gray first.
+    blur : dict | None, default={'fun': cv.GaussianBlur, 'ksize': (3, 3), \
+            'borderType': cv.BORDER_DEFAULT}
+        Spatial blur: cv.GaussianBlur or cv.blur and its parameters; None disables it.
+        As in the reference the third value is passed POSITIONALLY, so for cv.GaussianBlur it
+        is sigmaX (default 4.0) and for cv.blur it has no effect; borders are REFLECT_101.
+    frg_detect : {'MOG2', 'KNN', 'ViBe', 'FD'}, default='MOG2'
+        Foreground detection method.
+    mat_morph : list of dict | None
+        cv.erode / cv.dilate steps with their 'kernel'; default: 5x5 open.
+    tracking, post_filter, alarm_def, verbose :
+        as in the reference (pipeline.py:69-128).
+    device : int, default=0
+        CUDA device of this stream's pipeline.
+    knn_seed : int, default=0
+        State of the cv::RNG replica KNN draws from (0 = OpenCV's default state); the
+        reference consumes the calling thread's cv.theRNG() instead.
+
+    Attributes
+    ----------
+    foreground_mask_ : ndarray (H, W) uint8, fetched from the GPU when read.
+    blobs_ : list of dict(contour, anchor, bottom, center)
+    tracked_blobs_ : list of dict, see the reference.
+    """
+
+    def __init__(
+        self,
+        convert=None,
+        blur=_default_blur(),
+        frg_detect='MOG2',
+        mat_morph=_default_morph(),
+        tracking={'factor': 1.5, 'absence_max': 10},
+        post_filter={'perimeter': None, 'anchor': 'bottom', 'perspective': None,
+                     'perspective_coeff': 0.5, 'presence_min': 3, 'distance_min': 0.25},
+        alarm_def={'keep_alarm': True, 'duration_min': 10},
+        verbose=False,
+        device=0,
+        knn_seed=0,
+    ):
+        self.convert = convert
+        self.blur = blur
+        self.frg_detect = frg_detect
+        self.mat_morph = mat_morph
+        self.tracking = tracking
+        self.post_filter = post_filter
+        self.alarm_def = alarm_def
+        self.verbose = verbose
+        self.device = device
+        self.knn_seed = knn_seed
+
+    # ------------------------------------------------------------------ configuration
+    def initialize(self):
+        """Check the parameters and set the pipeline up (reference pipeline.py:214-283).
+
+        Raises KeyError for missing dictionary keys and ValueError for bad values, at the
+        same places as the reference."""
+        if self.blur:
+            if 'fun' not in self.blur.keys():
+                raise KeyError('Parameter blur has no key "fun".')
+            self.blur.setdefault('ksize', (3, 3))
+            self.blur.setdefault('borderType', _BORDER_DEFAULT)
+
+        if self.frg_detect not in ('MOG2', 'KNN', 'FD', 'ViBe'):
+            raise ValueError('Unknown method for foreground detection')
+
+        if self.mat_morph:
+            for d in self.mat_morph:
+                if 'fun' not in d.keys():
+                    raise KeyError('Parameter mat_morph has no key "fun".')
+                d.setdefault('kernel', _rect_kernel(5))
+
+        for key in ('factor', 'absence_max'):
+            if key not in self.tracking.keys():
+                raise KeyError('Parameter tracking has no key "%s".' % key)
+
+        if 'anchor' not in self.post_filter.keys():
+            raise KeyError('Parameter post_filter has no key "anchor".')
+        if self.post_filter['anchor'] not in ['bottom', 'center']:
+            raise ValueError('Parameter anchor must be "bottom" or "center".')
+        for key in ('perspective_coeff', 'presence_min', 'distance_min'):
+            if key not in self.post_filter.keys():
+                raise KeyError('Parameter post_filter has no key "%s".' % key)
+        self._check_perimeter()
+        self._check_perspective()
+
+        for key in ('keep_alarm', 'duration_min'):
+            if key not in self.alarm_def.keys():
+                raise KeyError('Parameter alarm_def has no key "%s".' % key)
+
+        self._plan = self._hot_path_plan()
+        self._engine = None           # created on the first frame (the shape is needed)
+        self._host_estimator = ViBe() if self.frg_detect == 'ViBe' else None
+        self._mask_cache = None
+        self.blobs_ = []
+        self.tracked_blobs_ = []
+        self.input_shape_ = None
+        self._alarm_system = {'already_in_alarm': False, 'duration': 0}
+        return self
+
+    def _hot_path_plan(self):
+        """Translate the reference's OpenCV-flavoured parameters into kernel configuration."""
+        blur = None
+        if self.blur:
+            name = _cv_name(self.blur.get('fun'))
+            ksize = tuple(int(k) for k in self.blur.get('ksize'))
+            if name == 'GaussianBlur':
+                # fun(X, ksize, borderType): the third positional argument of GaussianBlur is sigmaX
+                blur = ('gaussian', ksize, float(self.blur.get('borderType')))
+            elif name == 'blur':
+                blur = ('box', ksize)  # third positional argument of cv.blur is `dst`: ignored
+            else:
+                raise NotImplementedError(
+                    "blur['fun'] must be cv.GaussianBlur or cv.blur (the CUDA hot path has no "
+                    "CPU fallback for other callables): %r" % (self.blur.get('fun'),))
+        morph = []
+        for d in (self.mat_morph or []):
+            name = _cv_name(d.get('fun'))
+            if name not in ('erode', 'dilate'):
+                raise NotImplementedError(
+                    "mat_morph 'fun' must be cv.erode or cv.dilate: %r" % (d.get('fun'),))
+            morph.append((name, np.asarray(d.get('kernel'))))
+        return {'blur': blur, 'morph': morph}
+
+    def _check_perimeter(self):
+        pf = self.post_filter
+        if 'perimeter' not in pf.keys():
+            raise KeyError('Parameter post_filter has no key "perimeter".')
+        per = pf['perimeter']
+        if per is None:
+            pf['perimeter'] = np.array([[0, 0], [0, 1], [1, 1], [1, 0]])
+        elif isinstance(per, np.ndarray):
+            if per.ndim != 2:
+                raise ValueError('Parameter perimeter has not the good shape.')
+            if per.shape[0] < 3:
+                raise ValueError('Parameter perimeter has not enough points.')
+            if per.shape[1] != 2:
+                raise ValueError('Parameter perimeter has not the good shape.')
+        else:
+            raise ValueError('Unknown type for parameter "perimeter".')
+        if pf.get('display_config'):
+            pf['perimeter'] = self._config_perimeter()
+
+    def _check_perspective(self):
+        pf = self.post_filter
+        if 'perspective' not in pf.keys():
+            raise KeyError('Parameter post_filter has no key "perspective".')
+        per = pf['perspective']
+        if per is None:
+            pf['perspective'] = np.array([[0.1, 0.4], [0.2, 0.8], [0.8, 0.2], [0.85, 0.3]])
+        elif isinstance(per, np.ndarray):
+            if per.shape != (4, 2):
+                raise ValueError('Parameter perspective has not the good shape.')
+        else:
+            raise ValueError('Unknown type for parameter "perspective".')
+        if pf.get('display_config'):
+            pf['perspective'] = self._config_perspective()
+
+    # interactive configuration windows (reference pipeline.py:308-432) need an OpenCV GUI build
+    def _get_config_img(self):
+        pf = self.post_filter
+        if 'config_video_filename' in pf.keys():
+            img = read_first_frame(pf['config_video_filename'])
+        elif 'config_frame_filename' in pf.keys():
+            img = cv.imread(pf['config_frame_filename'])
+        elif 'config_frame' in pf.keys():
+            img = pf['config_frame']
+        else:
+            if self.verbose:
+                print("No configuration video or frame defined.")
+            img = 100 * np.ones((240, 320, 3), dtype=np.uint8)
+        if img is None:
+            raise ValueError('Configuration image is None.')
+        thickness = unnormalize_coords(np.array([[0.02, 0.02]]), img.shape, dtype=np.int32)[0]
+        return img, img.copy(), thickness
+
+    def _config_perimeter(self, window_name="Configure perimeter"):
+        from .gui import configure_perimeter
+        perimeter = configure_perimeter(self, window_name)
+        if self.verbose:
+            print("Config perimeter:\n", perimeter)
+        return perimeter
+
+    def _config_perspective(self, window_name="Configure perspective"):
+        from .gui import configure_perspective
+        perspective = configure_perspective(self, window_name)
+        if self.verbose:
+            print("Config perspective:\n", perspective)
+        return perspective
+
+    # ------------------------------------------------------------------ per frame
+    @property
+    def foreground_mask_(self):
+        """Foreground mask of the last frame, (H, W) uint8 (reference pipeline.py:476);
+        copied from the GPU on first access after each `detect`."""
+        if self._mask_cache is None and self._engine is not None:
+            self._mask_cache = self._engine.mask()
+        return self._mask_cache
+
+    def detect(self, X):
+        """Detect if there is an intrusion in the current frame.
+
+        Parameters
+        ----------
+        X : ndarray of uint8, shape (H, W) or (H, W, C)
+
+        Returns
+        -------
+        y : bool, intrusion detected.
+        """
+        if not self.input_shape_:
+            self.input_shape_ = X.shape
+            self._calib_first_frame()
+        elif X.shape != self.input_shape_:
+            raise ValueError('Input shape has changed.')
+
+        if self.convert:
+            X = self._convert(X)
+
+        # steps 1-4 on the GPU
+        if self._host_estimator is None:
+            self._hot_path(X)
+        else:
+            self._hot_path_host_estimator(X)
+
+        self._track_blob()       # step 5
+        self._post_filter()      # step 6
+        y = self._detect_blob()  # step 7
+        return self._maintain_alarm(y)
+
+    def _convert(self, X):
+        if self.convert in (_COLOR_BGR2GRAY, _COLOR_RGB2GRAY) and X.ndim == 3 and X.shape[2] == 3 \
+                and X.dtype == np.uint8:
+            return _to_gray(X, self.convert)
+        if cv is None:
+            raise NotImplementedError("colour conversion code %r needs OpenCV" % (self.convert,))
+        return cv.cvtColor(X, self.convert)  # a step before the hot path; other codes stay on cv2
+
+    def _new_engine(self, shape, detector, blur, morph):
+        from .hotpath import HotPath
+        if len(shape) == 3 and shape[2] == 1:
+            shape = shape[:2]
+        return HotPath(shape, blur=blur, detector=detector, morph=morph, area_min=100.0,
+                       device=self.device, knn_seed=self.knn_seed)
+
+    def _hot_path(self, X):
+        if self._engine is None:
+            self._engine = self._new_engine(X.shape, self.frg_detect, self._plan['blur'],
+                                            self._plan['morph'])
+        self._engine.process(X)
+        self._mask_cache = None
+        self.blobs_ = self._engine.blobs(anchor=self.post_filter['anchor'])
+
+    def _hot_path_host_estimator(self, X):
+        """ViBe keeps its host-side model (see segmentation.ViBe); blur before it and
+        morphology + blobs after it still run on the GPU."""
+        from .hotpath import HotPath
+        if self._engine is None:
+            shape = X.shape[:2] if (X.ndim == 3 and X.shape[2] == 1) else X.shape
+            self._pre = HotPath(shape, blur=self._plan['blur'], detector="FD", morph=(),
+                                find_blobs=False, device=self.device) if self._plan['blur'] else None
+            # masks are fed through frame differencing against an all-zero frame (|m - 0| > 0)
+            self._engine = HotPath(shape[:2], blur=None, detector="FD", morph=self._plan['morph'],
+                                   fd_threshold=0, area_min=100.0, device=self.device)
+        if self._pre is not None:
+            self._pre.process(X)
+            X = self._pre.fd_model()  # the blurred frame is FD's state
+        mask = self._host_estimator.apply(X)
+        self._engine.reset()
+        self._engine.process(np.zeros_like(mask))
+        self._engine.process(mask)
+        self._mask_cache = None
+        self.blobs_ = self._engine.blobs(anchor=self.post_filter['anchor'])
+
+    # ------------------------------------------------------------------ calibration
+    def _calib_first_frame(self):
+        """Turn the normalised perimeter / perspective into pixels (reference pipeline.py:495-547)."""
+        pf = self.post_filter
+        pf['perimeter'] = unnormalize_coords(pf['perimeter'], self.input_shape_, dtype=np.int32)
+        pf['perspective'] = unnormalize_coords(pf['perspective'], self.input_shape_, dtype=np.float64)
+        self._calib_perspective()
+
+    def _calib_perspective(self):
+        """Area, height and width of a person as linear functions of the bottom ordinate,
+        from the two calibration boxes."""
+        p = self.post_filter['perspective']
+        boxes = ((p[0], p[1]), (p[2], p[3]))
+        bottoms = [max(a[1], b[1]) for a, b in boxes]
+        heights = [abs(b[1] - a[1]) for a, b in boxes]
+        widths = [abs(b[0] - a[0]) for a, b in boxes]
+        areas = [h * w for h, w in zip(heights, widths)]
+        rows = np.arange(0, self.input_shape_[0], 1)
+        slr = SimpleLinearRegression()
+        self._perspective = {}
+        for key, values in (('area', areas), ('height', heights), ('width', widths)):
+            self._perspective[key] = slr.fit(bottoms, values).predict_clip(rows, 0)
+
+    def _predict_perspective(self, key, y):
+        y = np.clip(y, a_min=0, a_max=self.input_shape_[0] - 1)
+        return self._perspective.get(key)[y]
+
+    # ------------------------------------------------------------------ step 5: tracking
+    def _tracking_radii(self, bottom):
+        """Major / minor radius of the elliptic search region of a tracked blob."""
+        major = np.int32(self._predict_perspective('height', bottom[1]) * self.tracking['factor'])
+        return major, np.int32(major / 2)
+
+    def _tracking_distance(self, tracked, blob):
+        """Normalised elliptic distance (<= 1: inside the search region) between a tracked
+        blob and an instantaneous blob (reference pipeline.py:639-662)."""
+        r_maj, r_min = self._tracking_radii(tracked['bottom'])
+        if r_maj <= 0 or r_min <= 0:
+            return 0
+        dx = blob['center'][0] - tracked['center'][0]
+        dy = blob['center'][1] - tracked['center'][1]
+        return dx**2 / r_maj**2 + dy**2 / r_min**2
+
+    @staticmethod
+    def _new_track(blob):
+        return {'contour': blob['contour'].copy(), 'anchor': blob['anchor'], 'bottom': blob['bottom'],
+                'center': blob['center'], 'center_first': blob['center'], 'presence': 1, 'absence': 0,
+                'filtered': set(['presence', 'distance']), 'already_in_alarm': False}
+
+    def _relative_travel(self, track):
+        """Distance between first and last centre, in units of sqrt(expected person area)."""
+        delta = np.asarray(track['center'], dtype=np.float64) - np.asarray(track['center_first'],
+                                                                          dtype=np.float64)
+        area_min = self._predict_perspective('area', track['bottom'][1])
+        if area_min <= 0:
+            return 0
+        return float(np.sqrt((delta * delta).sum())) / np.sqrt(area_min)
+
+    def _pair(self, track, blob):
+        track.update(contour=blob['contour'].copy(), anchor=blob['anchor'], bottom=blob['bottom'],
+                     center=blob['center'], absence=0)
+        track['presence'] += 1
+        if track['presence'] >= self.post_filter['presence_min']:
+            track['filtered'].discard('presence')
+        if self._relative_travel(track) >= self.post_filter['distance_min']:
+            track['filtered'].discard('distance')
+
+    def _miss(self, j):
+        track = self.tracked_blobs_[j]
+        track['presence'] = 0
+        track['filtered'].add('presence')
+        track['absence'] += 1
+        if track['absence'] >= self.tracking['absence_max']:
+            self.tracked_blobs_.pop(j)
+
+    def _track_blob(self):
+        """Greedy nearest-track association in blob order (reference pipeline.py:590-628):
+        each blob takes the closest pre-existing track if it lies in that track's search
+        ellipse, otherwise it starts a new track; unmatched tracks age."""
+        blobs, tracks = self.blobs_, self.tracked_blobs_
+        n_tracks = len(tracks)
+        if n_tracks == 0:
+            tracks.extend(self._new_track(b) for b in blobs)
+            return
+        if not blobs:
+            for j in range(n_tracks - 1, -1, -1):
+                self._miss(j)
+            return
+        dist = np.array([[self._tracking_distance(tracks[j], b) for j in range(n_tracks)]
+                         for b in blobs], dtype=np.float64)
+        for i, blob in enumerate(blobs):
+            j = int(np.argmin(dist[i]))
+            if dist[i, j] <= 1:
+                dist[i, j] = -1  # marks the pair
+                self._pair(tracks[j], blob)
+            else:
+                tracks.append(self._new_track(blob))
+        for j in range(n_tracks - 1, -1, -1):
+            if np.all(dist[:, j] >= 0):
+                self._miss(j)
+
+    # ------------------------------------------------------------------ steps 6-7
+    def _post_filter(self):
+        """Perimeter and perspective filters on tracked blobs (reference pipeline.py:734-762)."""
+        pf = self.post_filter
+        for track in self.tracked_blobs_:
+            if point_in_polygon(pf['perimeter'], track['anchor']) < 0:
+                track['filtered'].add('perimeter')
+            else:
+                track['filtered'].discard('perimeter')
+            xy = track['contour'].reshape(-1, 2)
+            width = int(xy[:, 0].max()) - int(xy[:, 0].min()) + 1
+            height = int(xy[:, 1].max()) - int(xy[:, 1].min()) + 1
+            if width * height <= self._predict_perspective('area', track['bottom'][1]) * pf['perspective_coeff']:
+                track['filtered'].add('perspective')
+            else:
+                track['filtered'].discard('perspective')
+
+    def _detect_blob(self):
+        alarm = False
+        for track in self.tracked_blobs_:
+            if not track['filtered']:
+                alarm = True
+                if self.alarm_def['keep_alarm']:
+                    track['already_in_alarm'] = True
+            elif track['already_in_alarm']:
+                alarm = True
+        return alarm
+
+    def _maintain_alarm(self, sys_in_alarm):
+        """Hold a raised alarm for `duration_min` frames (reference pipeline.py:782-799)."""
+        state = self._alarm_system
+        state['duration'] -= 1
+        if sys_in_alarm and not state['already_in_alarm']:
+            state['duration'] = self.alarm_def['duration_min']
+        if not sys_in_alarm and state['duration'] >= 0:
+            sys_in_alarm = True
+        if self.verbose and sys_in_alarm and not state['already_in_alarm']:
+            print("Intrusion detected")
+        state['already_in_alarm'] = sys_in_alarm
+        return sys_in_alarm
+
+    # ------------------------------------------------------------------ on-screen display
+    def display(self, X, display={'tracking': False, 'perspective': False}):
+        """Draw the perimeter and the tracked blobs into `X` in place (reference
+        pipeline.py:801-853).  Needs OpenCV's drawing functions."""
+        if cv is None:
+            raise NotImplementedError("display() draws with OpenCV, which is not installed")
+        cv.drawContours(X, [self.post_filter['perimeter']], 0, (25, 200, 200))
+        for track in self.tracked_blobs_:
+            flt = track['filtered']
+            if not flt or track['already_in_alarm']:
+                color = (0, 0, 255)
+            elif 'perimeter' in flt:
+                color = (255, 0, 0)
+            elif 'perspective' in flt:
+                color = (25, 200, 200)
+            elif 'presence' in flt or 'distance' in flt:
+                color = (0, 255, 0)
+            else:
+                raise ValueError(f'Unknown filtering type {flt}')
+            cv.drawContours(X, [track['contour']], 0, color)
+            cv.circle(X, [int(v) for v in track['anchor']], 4, color, -1)
+            if display.get('tracking'):
+                r_maj, r_min = self._tracking_radii(track['bottom'])
+                cv.ellipse(X, [int(v) for v in track['center']], [int(r_maj), int(r_min)], 0, 0, 360,
+                           color, 1)
+            if display.get('perspective'):
+                h = int(self._predict_perspective('height', track['bottom'][1]))
+                w = int(self._predict_perspective('width', track['bottom'][1]))
+                bx, by = int(track['bottom'][0]), int(track['bottom'][1])
+                cv.rectangle(X, [bx - w // 2, by], [bx + w // 2, by - h], color, 1)

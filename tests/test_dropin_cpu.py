@@ -1,0 +1,141 @@
+"""CPU: the GOFPID drop-in's host logic -- parameter validation (same exception types as the
+reference, pipeline.py:214-306,355-373), helpers' known answers (reference tests/test_helpers.py)
+and the OpenCV-parameter -> kernel-configuration mapping.  No GPU needed: the CUDA pipeline is
+only created on the first frame."""
+import numpy as np
+import pytest
+
+from pygofpid_b200 import GOFPID
+from pygofpid_b200 import helpers as h
+
+try:
+    import cv2 as cv
+except Exception:
+    cv = None
+
+PF = {'perimeter': None, 'anchor': 'center', 'perspective': None, 'perspective_coeff': 0.5,
+      'presence_min': 3, 'distance_min': 0.25}
+
+
+def make(**kw):
+    kw.setdefault('post_filter', dict(PF))
+    return GOFPID(**kw)
+
+
+def test_initialize_returns_self_and_resets_state():
+    g = make()
+    assert g.initialize() is g
+    assert g.tracked_blobs_ == [] and g.input_shape_ is None and g.blobs_ == []
+    assert g.post_filter['perimeter'].shape == (4, 2) and g.post_filter['perspective'].shape == (4, 2)
+
+
+def test_blur_errors_and_defaults():
+    with pytest.raises(KeyError):
+        make(blur={'ksize': (3, 3)}).initialize()
+    g = make(blur={'fun': 'blur'}).initialize()
+    assert g.blur['ksize'] == (3, 3) and g.blur['borderType'] == 4
+    assert g._plan['blur'] == ('box', (3, 3))
+    assert make(blur=None).initialize()._plan['blur'] is None
+
+
+@pytest.mark.skipif(cv is None, reason="needs cv2 objects")
+def test_opencv_parameter_objects_map_to_kernel_config():
+    g = make(blur={'fun': cv.GaussianBlur, 'ksize': (5, 5), 'borderType': cv.BORDER_REPLICATE},
+             mat_morph=[{'fun': cv.dilate, 'kernel': cv.getStructuringElement(cv.MORPH_ELLIPSE, (15, 15))},
+                        {'fun': cv.erode}]).initialize()
+    assert g._plan['blur'] == ('gaussian', (5, 5), 1.0)  # borderType lands in sigmaX (reference quirk)
+    assert [m[0] for m in g._plan['morph']] == ['dilate', 'erode']
+    assert g._plan['morph'][0][1].shape == (15, 15) and g._plan['morph'][1][1].shape == (5, 5)
+    with pytest.raises(NotImplementedError):
+        make(blur={'fun': cv.medianBlur}).initialize()
+    with pytest.raises(NotImplementedError):
+        make(mat_morph=[{'fun': cv.morphologyEx}]).initialize()
+
+
+def test_detector_and_morph_errors():
+    with pytest.raises(ValueError):
+        make(frg_detect='blabla').initialize()
+    with pytest.raises(KeyError):
+        make(mat_morph=[{'kernel': np.ones((3, 3), np.uint8)}]).initialize()
+    for det in ('MOG2', 'KNN', 'FD', 'ViBe'):
+        make(frg_detect=det).initialize()
+
+
+def test_tracking_and_alarm_errors():
+    with pytest.raises(KeyError):
+        make(tracking={'absence_max': 10}).initialize()
+    with pytest.raises(KeyError):
+        make(tracking={'factor': 1.5}).initialize()
+    with pytest.raises(KeyError):
+        make(alarm_def={'duration_min': 10}).initialize()
+    with pytest.raises(KeyError):
+        make(alarm_def={'keep_alarm': True}).initialize()
+
+
+@pytest.mark.parametrize("drop", ['perimeter', 'anchor', 'perspective', 'perspective_coeff', 'presence_min',
+                                  'distance_min'])
+def test_post_filter_missing_keys(drop):
+    pf = dict(PF)
+    del pf[drop]
+    with pytest.raises(KeyError):
+        GOFPID(post_filter=pf).initialize()
+
+
+def test_post_filter_bad_values():
+    bad = [dict(PF, anchor='top'), dict(PF, perimeter=[[0, 0], [1, 1], [1, 0]]),
+           dict(PF, perimeter=np.zeros((4, 2, 1))), dict(PF, perimeter=np.zeros((2, 2))),
+           dict(PF, perimeter=np.zeros((4, 3))), dict(PF, perspective=[[0, 0]] * 4),
+           dict(PF, perspective=np.zeros((3, 2)))]
+    for pf in bad:
+        with pytest.raises(ValueError):
+            GOFPID(post_filter=pf).initialize()
+
+
+# ---- helpers: known answers of the reference's tests/test_helpers.py ----------------------------
+def test_find_point_and_line():
+    pts = np.array([[10, 10], [10, 50], [50, 50], [50, 10]])
+    th = np.array([3, 3])
+    assert h.find_point((11, 9), pts, th) == 0 and h.find_point((49, 52), pts, th) == 2
+    assert h.find_point((30, 30), pts, th) == -1
+    assert h.find_line((10, 30), pts, th) == 0 and h.find_line((30, 50), pts, th) == 1
+    assert h.find_line((30, 30), pts, th) == -1 and h.find_line((1, 1), pts[:1], th) == -1
+
+
+def test_bottom_center_of_square_contour():
+    c = np.array([[[0, 0]], [[0, 10]], [[10, 10]], [[10, 0]]], np.int32)
+    assert np.array_equal(h.get_bottom(c), [5, 10]) and h.get_bottom(c).dtype == np.int16
+    assert np.array_equal(h.get_center(c), [5, 5])
+
+
+def test_coords_roundtrip_and_regression():
+    shape = (240, 320, 3)
+    c = np.array([[32, 24], [160, 120]])
+    n = h.normalize_coords(c, shape)
+    assert np.allclose(n, [[0.1, 0.1], [0.5, 0.5]])
+    assert np.array_equal(h.unnormalize_coords(n, shape), c)
+    assert c.dtype.kind == 'i'  # inputs are not modified
+    slr = h.SimpleLinearRegression().fit([0, 10], [1, 21])
+    assert slr.coeff == 2 and slr.intercept == 1
+    assert np.allclose(slr.predict([0, 5]), [1, 11])
+    assert np.allclose(slr.predict_clip([-5, 5], 0), [0, 11])
+    with pytest.raises(ValueError):
+        slr.fit([0, 1, 2], [0, 1, 2])
+    with pytest.raises(ValueError):
+        slr.fit([0, 1], [0, 1, 2])
+
+
+def test_cdist_and_dist():
+    a, b = np.array([[0, 0], [3, 4]]), np.array([[0, 0], [6, 8], [3, 4]])
+    d = h.cdist_euclidean(a, b)
+    assert d.shape == (2, 3) and np.allclose(d, [[0, 10, 5], [5, 5, 0]])
+    assert h.dist_euclidean(3, 7) == 4 and np.isclose(h.dist_euclidean(np.array([0, 0]), np.array([3, 4])), 5)
+    assert h.change_extension("clip.avi") == "clip.png"
+
+
+@pytest.mark.skipif(cv is None, reason="needs cv2")
+def test_point_in_polygon_matches_cv2():
+    rs = np.random.RandomState(3)
+    poly = np.array([[2, 3], [40, 5], [35, 30], [20, 18], [5, 28]], np.int32)
+    for _ in range(2000):
+        p = (int(rs.randint(0, 45)), int(rs.randint(0, 35)))
+        assert h.point_in_polygon(poly, p) == cv.pointPolygonTest(poly, p, False)
