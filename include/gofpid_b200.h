@@ -164,7 +164,17 @@ GOFPID_API int gofpid_pipeline_process_device(gofpid_pipeline *p, const uint8_t 
 GOFPID_API int gofpid_pipeline_process_host(gofpid_pipeline *p, const uint8_t *h_frames,
                                             size_t pitch, size_t stream_stride);
 
-/* Results of the last step (host copies; these synchronise with the pipeline's stream). */
+/* Asynchronous variant of process_host for pinned host frames: enqueues the host->device copy
+ * and the step and returns; up to two frames are in flight (labelling / tracing of frame t
+ * overlaps the model update of frame t+1).  Results are collected later with the getters
+ * below, after gofpid_pipeline_select(p, 1) for the frame before the newest one. */
+GOFPID_API int gofpid_pipeline_submit_host(gofpid_pipeline *p, const uint8_t *h_frames,
+                                           size_t pitch, size_t stream_stride);
+/* Which frame the result getters refer to: age 0 = newest submitted frame (default after every
+ * process/submit call), 1 = the one before it. */
+GOFPID_API int gofpid_pipeline_select(gofpid_pipeline *p, int age);
+
+/* Results of the selected frame (host copies; these wait for that frame's kernels). */
 GOFPID_API int gofpid_pipeline_frame_info(gofpid_pipeline *p, int stream_idx,
                                           gofpid_frame_info *h_info);
 /* Blobs in the reference's order (descending raster order of the first pixel) and their

@@ -30,21 +30,45 @@ void set_error(const char *fmt, ...)
 
 using namespace gofpid;
 
+// Two frames are in flight at most: stage A (tick, blur+detect, morphology) of frame t+1 runs
+// on the caller's stream while stage B (labelling, statistics, border tracing) of frame t runs
+// on an internal stream.  The temporal model makes stage A strictly sequential; stage B only
+// needs the finished mask of its own frame, so consecutive frames of ONE camera stream overlap.
+constexpr int DEPTH = 2;
+
+struct FrameSlot {
+    uint8_t *d_final = nullptr;   // final mask of the frame in this slot
+    BlobBuffers blobs = {};
+    cudaEvent_t ev_mask = nullptr, ev_blobs = nullptr; // stage A / stage B of this slot finished
+    gofpid_frame_info *h_info = nullptr;               // pinned host copies of the results
+    gofpid_blob *h_kept = nullptr;
+    int32_t *h_points = nullptr;
+    uint8_t *d_frames = nullptr;  // staging of host frames
+    cudaEvent_t ev_h2d = nullptr;
+    bool used = false, fetched = false;
+    int frame_index = 0;
+    // stage graphs of this slot (buffers are baked into the kernel arguments)
+    cudaGraph_t graph_a = nullptr, graph_b = nullptr;
+    cudaGraphExec_t exec_a = nullptr, exec_b = nullptr;
+    cudaGraphNode_t tick_node = nullptr;
+};
+
 struct gofpid_pipeline {
     gofpid_config cfg;
     std::vector<std::vector<uint8_t>> se_copies;
     int H = 0, W = 0, C = 0, n_streams = 0, device = 0;
-    cudaStream_t stream = nullptr;     // own stream (process_host, fetches)
-    cudaStream_t last_stream = nullptr; // stream of the last process call
+    cudaStream_t stream = nullptr;   // own stage-A stream (host entry points)
+    cudaStream_t stream_b = nullptr; // stage B
+    cudaStream_t stream_c = nullptr; // result fetches
+    cudaStream_t stream_h = nullptr; // host->device frame copies
     BlurParams blur;
     Mog2Params mog2p;
     KnnParams knnp;
     int fd_thr = 0;
 
     FrameTick *d_tick = nullptr;
-    uint8_t *d_mask[2] = {nullptr, nullptr};
+    uint8_t *d_mask_det = nullptr; // detector output when a morphology chain follows
     size_t mask_pitch = 0, mask_stream = 0;
-    int final_mask = 0;
 
     Mog2Model mog2 = {};
     KnnModel knn = {};
@@ -54,30 +78,17 @@ struct gofpid_pipeline {
     uint64_t *d_pow2tab = nullptr;
 
     MorphPlan morph = {};
-    BlobBuffers blobs = {};
+    FrameSlot slots[DEPTH];
+    long frames = 0;  // frames submitted so far
+    int selected = 0; // age of the frame the result getters refer to (0 newest, 1 previous)
 
-    // host-side staging
-    uint8_t *d_frames = nullptr;
     size_t frames_pitch = 0, frames_stream = 0;
-    uint8_t *h_frames = nullptr; // pinned
-
-    // fetched results (pinned)
-    gofpid_frame_info *h_info = nullptr;
-    gofpid_blob *h_kept = nullptr;  // n_streams * max_kept
-    int32_t *h_points = nullptr;    // n_streams * max_points * 2
-    bool results_valid = false;     // host copies correspond to the last step
-    bool stepped = false;
+    uint8_t *h_frames = nullptr; // pinned staging for pageable input
 
     bool profiling = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     int launch_count = 0;
-
-    // the step as a CUDA graph: captured once, replayed per frame; only the tick kernel's
-    // arguments (where the frames are) change between launches
     bool use_graph = true;
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t graph_exec = nullptr;
-    cudaGraphNode_t tick_node = nullptr;
     TickArgs tick_args;
     int graph_launches = 0;
 };
@@ -138,61 +149,79 @@ int alloc_zero(void **ptr, size_t bytes)
     return GOFPID_OK;
 }
 
+// the slot of the frame the getters refer to (nullptr: no such frame yet)
+FrameSlot *selected_slot(gofpid_pipeline *p)
+{
+    const long idx = p->frames - 1 - p->selected;
+    if (idx < 0) return nullptr;
+    FrameSlot *S = &p->slots[idx % DEPTH];
+    return S->used ? S : nullptr;
+}
+
 int reset_state(gofpid_pipeline *p)
 {
     FrameTick t;
     memset(&t, 0, sizeof(t));
     t.knn_rng = p->cfg.knn_rng_seed ? p->cfg.knn_rng_seed : 0xffffffffULL;
     GOFPID_CUDA_TRY(cudaMemcpy(p->d_tick, &t, sizeof(t), cudaMemcpyHostToDevice));
-    const size_t npl = p->mog2.plane_elems;
     if (p->cfg.detector == GOFPID_DETECT_MOG2) {
-        GOFPID_CUDA_TRY(cudaMemset(p->mog2.nmodes, 0, npl * p->n_streams));
+        GOFPID_CUDA_TRY(cudaMemset(p->mog2.nmodes, 0, p->mog2.plane_elems * p->n_streams));
     } else if (p->cfg.detector == GOFPID_DETECT_KNN) {
         const size_t pe = p->knn.plane_elems;
         GOFPID_CUDA_TRY(cudaMemset(p->knn.samples, 0, pe * 21 * (p->C + 1) * p->n_streams));
         GOFPID_CUDA_TRY(cudaMemset(p->knn.nxt, 0, pe * sizeof(uint32_t) * p->n_streams));
         GOFPID_CUDA_TRY(cudaMemset(p->knn.idx, 0, pe * sizeof(uint16_t) * p->n_streams));
     }
-    p->results_valid = false;
-    p->stepped = false;
+    for (auto &S : p->slots) { S.used = false; S.fetched = false; S.frame_index = 0; }
+    p->frames = 0;
+    p->selected = 0;
     return GOFPID_OK;
 }
 
 void free_all(gofpid_pipeline *p)
 {
     cudaFree(p->d_tick);
-    cudaFree(p->d_mask[0]); cudaFree(p->d_mask[1]);
+    cudaFree(p->d_mask_det);
     cudaFree(p->mog2.planes); cudaFree(p->mog2.nmodes);
     cudaFree(p->knn.samples); cudaFree(p->knn.nxt); cudaFree(p->knn.idx); cudaFree(p->knn.fresh);
     cudaFree(p->fd.prev);
     cudaFree(p->d_knn_table); cudaFree(p->d_pow2tab);
     morph_plan_destroy(&p->morph);
-    cudaFree(p->blobs.labels); cudaFree(p->blobs.slot); cudaFree(p->blobs.comp); cudaFree(p->blobs.bitimg);
-    cudaFree(p->blobs.info); cudaFree(p->blobs.cand); cudaFree(p->blobs.kept); cudaFree(p->blobs.points);
-    cudaFree(p->d_frames);
+    for (auto &S : p->slots) {
+        cudaFree(S.d_final);
+        cudaFree(S.blobs.labels); cudaFree(S.blobs.slot); cudaFree(S.blobs.comp); cudaFree(S.blobs.bitimg);
+        cudaFree(S.blobs.info); cudaFree(S.blobs.kept); cudaFree(S.blobs.points);
+        cudaFree(S.d_frames);
+        if (S.h_info) cudaFreeHost(S.h_info);
+        if (S.h_kept) cudaFreeHost(S.h_kept);
+        if (S.h_points) cudaFreeHost(S.h_points);
+        if (S.ev_mask) cudaEventDestroy(S.ev_mask);
+        if (S.ev_blobs) cudaEventDestroy(S.ev_blobs);
+        if (S.ev_h2d) cudaEventDestroy(S.ev_h2d);
+        if (S.exec_a) cudaGraphExecDestroy(S.exec_a);
+        if (S.exec_b) cudaGraphExecDestroy(S.exec_b);
+        if (S.graph_a) cudaGraphDestroy(S.graph_a);
+        if (S.graph_b) cudaGraphDestroy(S.graph_b);
+    }
     if (p->h_frames) cudaFreeHost(p->h_frames);
-    if (p->h_info) cudaFreeHost(p->h_info);
-    if (p->h_kept) cudaFreeHost(p->h_kept);
-    if (p->h_points) cudaFreeHost(p->h_points);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
-    if (p->graph_exec) cudaGraphExecDestroy(p->graph_exec);
-    if (p->graph) cudaGraphDestroy(p->graph);
-    if (p->stream) cudaStreamDestroy(p->stream);
+    for (cudaStream_t s : {p->stream, p->stream_b, p->stream_c, p->stream_h})
+        if (s) cudaStreamDestroy(s);
 }
 
 int build(gofpid_pipeline *p)
 {
     const gofpid_config &cfg = p->cfg;
     const int H = p->H, W = p->W, C = p->C, S = p->n_streams;
-    GOFPID_CUDA_TRY(cudaStreamCreateWithFlags(&p->stream, cudaStreamNonBlocking));
+    for (cudaStream_t *s : {&p->stream, &p->stream_b, &p->stream_c, &p->stream_h})
+        GOFPID_CUDA_TRY(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking));
     for (auto &e : p->ev) GOFPID_CUDA_TRY(cudaEventCreate(&e));
     GOFPID_TRY(make_blur_params(cfg.blur_kind, cfg.blur_kw, cfg.blur_kh, cfg.blur_sigma, &p->blur));
 
     GOFPID_TRY(alloc_zero((void **)&p->d_tick, sizeof(FrameTick)));
     p->mask_pitch = round_up((size_t)W, 128);
     p->mask_stream = p->mask_pitch * H;
-    GOFPID_TRY(alloc_zero((void **)&p->d_mask[0], p->mask_stream * S));
-    GOFPID_TRY(alloc_zero((void **)&p->d_mask[1], p->mask_stream * S));
+    if (cfg.n_morph > 0) GOFPID_TRY(alloc_zero((void **)&p->d_mask_det, p->mask_stream * S));
 
     const int PW = (int)round_up((size_t)W, 32);
     const size_t pe = (size_t)PW * H;
@@ -255,22 +284,30 @@ int build(gofpid_pipeline *p)
     }
 
     GOFPID_TRY(morph_plan_create(p->cfg.morph, p->cfg.n_morph, &p->morph));
-    p->final_mask = p->cfg.n_morph > 0 ? 1 : 0;
 
     if (cfg.find_blobs) {
-        BlobBuffers &B = p->blobs;
-        B.max_blobs = cfg.max_blobs; B.max_kept = cfg.max_kept; B.max_points = cfg.max_points;
-        B.area_min = cfg.blob_area_min;
-        if (B.max_blobs < 1 || B.max_kept < 1 || B.max_points < 1) {
+        if (cfg.max_blobs < 1 || cfg.max_kept < 1 || cfg.max_points < 1) {
             set_error("blob capacities must be positive");
             return GOFPID_ERR_INVALID;
         }
+        if (W > 8191 || H > 32767) { set_error("frames beyond 8191 x 32767 are not supported by the border tracer"); return GOFPID_ERR_UNSUPPORTED; }
+        if (round_up((size_t)W, 4) * H >= (size_t)0x7fffffff) { set_error("frame too large for int32 labels"); return GOFPID_ERR_UNSUPPORTED; }
+    }
+    for (auto &F : p->slots) {
+        GOFPID_TRY(alloc_zero((void **)&F.d_final, p->mask_stream * S));
+        GOFPID_CUDA_TRY(cudaEventCreateWithFlags(&F.ev_mask, cudaEventDisableTiming));
+        GOFPID_CUDA_TRY(cudaEventCreateWithFlags(&F.ev_blobs, cudaEventDisableTiming));
+        GOFPID_CUDA_TRY(cudaEventCreateWithFlags(&F.ev_h2d, cudaEventDisableTiming));
+        GOFPID_CUDA_TRY(cudaMallocHost(&F.h_info, sizeof(gofpid_frame_info) * S));
+        memset(F.h_info, 0, sizeof(gofpid_frame_info) * S);
+        if (!cfg.find_blobs) continue;
+        BlobBuffers &B = F.blobs;
+        B.max_blobs = cfg.max_blobs; B.max_kept = cfg.max_kept; B.max_points = cfg.max_points;
+        B.area_min = cfg.blob_area_min;
         B.labels_pitch = round_up((size_t)W, 4);
         B.labels_stream = B.labels_pitch * H;
-        if (B.labels_stream >= (size_t)0x7fffffff) { set_error("frame too large for int32 labels"); return GOFPID_ERR_UNSUPPORTED; }
         GOFPID_TRY(alloc_zero((void **)&B.labels, B.labels_stream * sizeof(int32_t) * S));
         GOFPID_TRY(alloc_zero((void **)&B.slot, B.labels_stream * sizeof(int32_t) * S));
-        if (W > 8191 || H > 32767) { set_error("frames beyond 8191 x 32767 are not supported by the border tracer"); return GOFPID_ERR_UNSUPPORTED; }
         B.bit_pitch = (int)round_up((size_t)(W + 31) / 32 + 2, 4);
         B.bit_stream = (size_t)B.bit_pitch * (H + 2);
         GOFPID_TRY(alloc_zero((void **)&B.bitimg, B.bit_stream * sizeof(uint32_t) * S));
@@ -278,16 +315,15 @@ int build(gofpid_pipeline *p)
         GOFPID_TRY(alloc_zero((void **)&B.info, sizeof(gofpid_frame_info) * S));
         GOFPID_TRY(alloc_zero((void **)&B.kept, sizeof(gofpid_blob) * B.max_kept * S));
         GOFPID_TRY(alloc_zero((void **)&B.points, sizeof(int32_t) * 2 * B.max_points * S));
-        GOFPID_CUDA_TRY(cudaMallocHost(&p->h_kept, sizeof(gofpid_blob) * B.max_kept * S));
-        GOFPID_CUDA_TRY(cudaMallocHost(&p->h_points, sizeof(int32_t) * 2 * B.max_points * S));
+        GOFPID_CUDA_TRY(cudaMallocHost(&F.h_kept, sizeof(gofpid_blob) * B.max_kept * S));
+        GOFPID_CUDA_TRY(cudaMallocHost(&F.h_points, sizeof(int32_t) * 2 * B.max_points * S));
     }
-    GOFPID_CUDA_TRY(cudaMallocHost(&p->h_info, sizeof(gofpid_frame_info) * S));
-    memset(p->h_info, 0, sizeof(gofpid_frame_info) * S);
     return reset_state(p);
 }
 
-// Enqueues the kernels of one step on `s` (also used under stream capture).
-int enqueue_step(gofpid_pipeline *p, const FrameSrc &src, cudaStream_t s, bool prof, int *n_launches)
+// ---- stage A: tick, blur + detect, morphology -> the slot's final mask -------------------------
+int enqueue_stage_a(gofpid_pipeline *p, FrameSlot &F, const FrameSrc &src, cudaStream_t s, bool prof,
+                    int *n_launches)
 {
     int launches = 0;
     if (prof) GOFPID_CUDA_TRY(cudaEventRecord(p->ev[0], s));
@@ -298,7 +334,7 @@ int enqueue_step(gofpid_pipeline *p, const FrameSrc &src, cudaStream_t s, bool p
     L.H = p->H; L.W = p->W; L.C = p->C; L.n_streams = p->n_streams;
     L.src = src;
     L.blur = p->blur;
-    L.mask = ImageU8{p->d_mask[0], p->mask_pitch, p->mask_stream};
+    L.mask = ImageU8{p->cfg.n_morph > 0 ? p->d_mask_det : F.d_final, p->mask_pitch, p->mask_stream};
     L.tick = p->d_tick;
     L.stream = s;
     if (p->cfg.detector == GOFPID_DETECT_MOG2) GOFPID_TRY(launch_mog2(L, p->mog2, p->mog2p));
@@ -307,119 +343,192 @@ int enqueue_step(gofpid_pipeline *p, const FrameSrc &src, cudaStream_t s, bool p
     launches += detect_launches_per_step(p->cfg.detector);
     if (prof) GOFPID_CUDA_TRY(cudaEventRecord(p->ev[1], s));
     if (p->cfg.n_morph > 0) {
-        GOFPID_TRY(launch_morph(p->morph, L.mask, ImageU8{p->d_mask[1], p->mask_pitch, p->mask_stream},
+        GOFPID_TRY(launch_morph(p->morph, L.mask, ImageU8{F.d_final, p->mask_pitch, p->mask_stream},
                                 p->H, p->W, p->n_streams, s));
         launches += 1;
     }
     if (prof) GOFPID_CUDA_TRY(cudaEventRecord(p->ev[2], s));
-    if (p->cfg.find_blobs) {
-        int nb = 0;
-        GOFPID_TRY(launch_blobs(p->blobs, ImageU8{p->d_mask[p->final_mask], p->mask_pitch, p->mask_stream},
-                                p->H, p->W, p->n_streams, p->d_tick, s, &nb));
-        launches += nb;
-    }
-    if (prof) GOFPID_CUDA_TRY(cudaEventRecord(p->ev[3], s));
     if (n_launches) *n_launches = launches;
     return GOFPID_OK;
 }
 
-// Captures the step once (on the pipeline's own stream) and finds the tick kernel's node.
-int build_graph(gofpid_pipeline *p, const FrameSrc &src)
+// ---- stage B: labelling, statistics, border tracing on the slot's final mask ---------------------
+int enqueue_stage_b(gofpid_pipeline *p, FrameSlot &F, cudaStream_t s, int *n_launches)
 {
-    // a plain launch first: sets the per-function attributes (dynamic smem opt-in) outside capture
-    int launches = 0;
+    int nb = 0;
+    if (p->cfg.find_blobs)
+        GOFPID_TRY(launch_blobs(F.blobs, ImageU8{F.d_final, p->mask_pitch, p->mask_stream}, p->H, p->W,
+                                p->n_streams, nullptr, s, &nb));
+    if (n_launches) *n_launches = nb;
+    return GOFPID_OK;
+}
+
+// Captures the two stage graphs of a slot (on the pipeline's own streams; nothing executes).
+int build_graphs(gofpid_pipeline *p, FrameSlot &F, const FrameSrc &src)
+{
+    int la = 0, lb = 0;
     GOFPID_CUDA_TRY(cudaStreamBeginCapture(p->stream, cudaStreamCaptureModeThreadLocal));
-    int rc = enqueue_step(p, src, p->stream, false, &launches);
-    cudaGraph_t g = nullptr;
-    cudaError_t e = cudaStreamEndCapture(p->stream, &g);
-    if (rc != GOFPID_OK) { if (g) cudaGraphDestroy(g); return rc; }
-    if (e != cudaSuccess) { set_error("graph capture failed: %s", cudaGetErrorString(e)); return GOFPID_ERR_CUDA; }
-    p->graph = g;
+    int rc = enqueue_stage_a(p, F, src, p->stream, false, &la);
+    cudaError_t e = cudaStreamEndCapture(p->stream, &F.graph_a);
+    if (rc != GOFPID_OK) return rc;
+    if (e != cudaSuccess) { set_error("graph capture (stage A) failed: %s", cudaGetErrorString(e)); return GOFPID_ERR_CUDA; }
     size_t n = 0;
-    GOFPID_CUDA_TRY(cudaGraphGetNodes(g, nullptr, &n));
+    GOFPID_CUDA_TRY(cudaGraphGetNodes(F.graph_a, nullptr, &n));
     std::vector<cudaGraphNode_t> nodes(n);
-    GOFPID_CUDA_TRY(cudaGraphGetNodes(g, nodes.data(), &n));
-    p->tick_node = nullptr;
+    GOFPID_CUDA_TRY(cudaGraphGetNodes(F.graph_a, nodes.data(), &n));
+    F.tick_node = nullptr;
     for (size_t i = 0; i < n; i++) {
         cudaGraphNodeType t;
         GOFPID_CUDA_TRY(cudaGraphNodeGetType(nodes[i], &t));
         if (t != cudaGraphNodeTypeKernel) continue;
         cudaKernelNodeParams kp;
         GOFPID_CUDA_TRY(cudaGraphKernelNodeGetParams(nodes[i], &kp));
-        if (kp.func == tick_kernel_func()) { p->tick_node = nodes[i]; break; }
+        if (kp.func == tick_kernel_func()) { F.tick_node = nodes[i]; break; }
     }
-    if (!p->tick_node) { set_error("graph capture: tick node not found"); return GOFPID_ERR_CUDA; }
-    GOFPID_CUDA_TRY(cudaGraphInstantiate(&p->graph_exec, g, 0));
-    p->graph_launches = launches;
+    if (!F.tick_node) { set_error("graph capture: tick node not found"); return GOFPID_ERR_CUDA; }
+    GOFPID_CUDA_TRY(cudaGraphInstantiate(&F.exec_a, F.graph_a, 0));
+    if (p->cfg.find_blobs) {
+        GOFPID_CUDA_TRY(cudaStreamBeginCapture(p->stream_b, cudaStreamCaptureModeThreadLocal));
+        rc = enqueue_stage_b(p, F, p->stream_b, &lb);
+        e = cudaStreamEndCapture(p->stream_b, &F.graph_b);
+        if (rc != GOFPID_OK) return rc;
+        if (e != cudaSuccess) { set_error("graph capture (stage B) failed: %s", cudaGetErrorString(e)); return GOFPID_ERR_CUDA; }
+        GOFPID_CUDA_TRY(cudaGraphInstantiate(&F.exec_b, F.graph_b, 0));
+    }
+    p->graph_launches = la + lb;
     return GOFPID_OK;
 }
 
+// One time step: stage A on `s`, stage B on the internal stream.
 int run_step(gofpid_pipeline *p, const uint8_t *d_frames, size_t pitch, size_t stream_stride,
              cudaStream_t s)
 {
     const FrameSrc src{d_frames, pitch, stream_stride};
-    int launches = 0;
-    if (p->use_graph && !p->profiling && p->stepped) {
-        // (the very first step runs eagerly: it also performs the one-time function setup)
-        if (!p->graph_exec) GOFPID_TRY(build_graph(p, src));
-        p->tick_args.src = src;
-        void *params[10];
-        tick_kernel_params(p->tick_args, params);
-        cudaKernelNodeParams kp = {};
-        kp.func = const_cast<void *>(tick_kernel_func());
-        kp.gridDim = dim3(1); kp.blockDim = dim3(32); kp.sharedMemBytes = 0;
-        kp.kernelParams = params; kp.extra = nullptr;
-        GOFPID_CUDA_TRY(cudaGraphExecKernelNodeSetParams(p->graph_exec, p->tick_node, &kp));
-        GOFPID_CUDA_TRY(cudaGraphLaunch(p->graph_exec, s));
-        launches = p->graph_launches;
+    FrameSlot &F = p->slots[p->frames % DEPTH];
+    int la = 0, lb = 0;
+    // the slot's previous frame (t - DEPTH) must be done with its mask before it is overwritten
+    if (F.used) GOFPID_CUDA_TRY(cudaStreamWaitEvent(s, F.ev_blobs, 0));
+    if (p->profiling) {
+        // everything on one stream, with events between the stages
+        GOFPID_TRY(enqueue_stage_a(p, F, src, s, true, &la));
+        GOFPID_TRY(enqueue_stage_b(p, F, s, &lb));
+        GOFPID_CUDA_TRY(cudaEventRecord(p->ev[3], s));
+        GOFPID_CUDA_TRY(cudaEventRecord(F.ev_mask, s));
+        GOFPID_CUDA_TRY(cudaEventRecord(F.ev_blobs, s));
     } else {
-        GOFPID_TRY(enqueue_step(p, src, s, p->profiling, &launches));
+        // (the first DEPTH steps run eagerly: they also perform the one-time function setup)
+        const bool graph = p->use_graph && p->frames >= DEPTH;
+        if (graph && !F.exec_a) GOFPID_TRY(build_graphs(p, F, src));
+        if (graph) {
+            p->tick_args.src = src;
+            void *params[10];
+            tick_kernel_params(p->tick_args, params);
+            cudaKernelNodeParams kp = {};
+            kp.func = const_cast<void *>(tick_kernel_func());
+            kp.gridDim = dim3(1); kp.blockDim = dim3(32); kp.sharedMemBytes = 0;
+            kp.kernelParams = params; kp.extra = nullptr;
+            GOFPID_CUDA_TRY(cudaGraphExecKernelNodeSetParams(F.exec_a, F.tick_node, &kp));
+            GOFPID_CUDA_TRY(cudaGraphLaunch(F.exec_a, s));
+            la = p->graph_launches;
+        } else {
+            GOFPID_TRY(enqueue_stage_a(p, F, src, s, false, &la));
+        }
+        GOFPID_CUDA_TRY(cudaEventRecord(F.ev_mask, s));
+        if (p->cfg.find_blobs) {
+            GOFPID_CUDA_TRY(cudaStreamWaitEvent(p->stream_b, F.ev_mask, 0));
+            if (graph) GOFPID_CUDA_TRY(cudaGraphLaunch(F.exec_b, p->stream_b));
+            else GOFPID_TRY(enqueue_stage_b(p, F, p->stream_b, &lb));
+            GOFPID_CUDA_TRY(cudaEventRecord(F.ev_blobs, p->stream_b));
+        } else {
+            GOFPID_CUDA_TRY(cudaEventRecord(F.ev_blobs, s));
+        }
     }
-    p->launch_count = launches;
-    p->last_stream = s;
-    p->results_valid = false;
-    p->stepped = true;
+    p->launch_count = la + lb;
+    F.used = true;
+    F.fetched = false;
+    F.frame_index = (int)(++p->frames);
+    p->selected = 0;
     return GOFPID_OK;
 }
 
-// Brings the per-stream headers, kept blobs and contour points of the last step to the host.
-int fetch_results(gofpid_pipeline *p)
+// Brings the per-stream headers, kept blobs and contour points of a slot's frame to the host.
+int fetch_results(gofpid_pipeline *p, FrameSlot *F)
 {
-    if (p->results_valid) return GOFPID_OK;
-    if (!p->stepped) { set_error("no frame has been processed yet"); return GOFPID_ERR_INVALID; }
-    cudaStream_t s = p->last_stream;
+    if (!F) { set_error("no frame has been processed yet"); return GOFPID_ERR_INVALID; }
+    if (F->fetched) return GOFPID_OK;
     const int S = p->n_streams;
+    GOFPID_CUDA_TRY(cudaEventSynchronize(F->ev_blobs));
     if (!p->cfg.find_blobs) {
-        GOFPID_CUDA_TRY(cudaStreamSynchronize(s));
-        FrameTick t;
-        GOFPID_CUDA_TRY(cudaMemcpy(&t, p->d_tick, sizeof(t), cudaMemcpyDeviceToHost));
-        for (int z = 0; z < S; z++) { memset(&p->h_info[z], 0, sizeof(gofpid_frame_info)); p->h_info[z].frame_index = t.nframes; }
-        p->results_valid = true;
+        for (int z = 0; z < S; z++) { memset(&F->h_info[z], 0, sizeof(gofpid_frame_info)); F->h_info[z].frame_index = F->frame_index; }
+        F->fetched = true;
         return GOFPID_OK;
     }
-    GOFPID_CUDA_TRY(cudaMemcpyAsync(p->h_info, p->blobs.info, sizeof(gofpid_frame_info) * S,
-                                    cudaMemcpyDeviceToHost, s));
+    cudaStream_t s = p->stream_c;
+    const BlobBuffers &B = F->blobs;
+    GOFPID_CUDA_TRY(cudaMemcpyAsync(F->h_info, B.info, sizeof(gofpid_frame_info) * S, cudaMemcpyDeviceToHost, s));
     GOFPID_CUDA_TRY(cudaStreamSynchronize(s));
     bool any = false;
     for (int z = 0; z < S; z++) {
-        const int nk = std::min(p->h_info[z].n_kept, p->blobs.max_kept);
-        const int np = std::min(p->h_info[z].n_points, p->blobs.max_points);
+        F->h_info[z].frame_index = F->frame_index;
+        const int nk = std::min(F->h_info[z].n_kept, B.max_kept);
+        const int np = std::min(F->h_info[z].n_points, B.max_points);
         if (nk > 0) {
-            GOFPID_CUDA_TRY(cudaMemcpyAsync(p->h_kept + (size_t)z * p->blobs.max_kept,
-                                            p->blobs.kept + (size_t)z * p->blobs.max_kept,
+            GOFPID_CUDA_TRY(cudaMemcpyAsync(F->h_kept + (size_t)z * B.max_kept, B.kept + (size_t)z * B.max_kept,
                                             sizeof(gofpid_blob) * nk, cudaMemcpyDeviceToHost, s));
             any = true;
         }
         if (np > 0) {
-            GOFPID_CUDA_TRY(cudaMemcpyAsync(p->h_points + (size_t)z * p->blobs.max_points * 2,
-                                            p->blobs.points + (size_t)z * p->blobs.max_points * 2,
+            GOFPID_CUDA_TRY(cudaMemcpyAsync(F->h_points + (size_t)z * B.max_points * 2,
+                                            B.points + (size_t)z * B.max_points * 2,
                                             sizeof(int32_t) * 2 * np, cudaMemcpyDeviceToHost, s));
             any = true;
         }
     }
     if (any) GOFPID_CUDA_TRY(cudaStreamSynchronize(s));
-    p->results_valid = true;
+    F->fetched = true;
     return GOFPID_OK;
+}
+
+// Host frames -> the slot's staging buffer (asynchronous when the source is pinned), then the step.
+int submit_host(gofpid_pipeline *p, const uint8_t *h_frames, size_t pitch, size_t stream_stride)
+{
+    const size_t row = (size_t)p->W * p->C;
+    if (pitch < row) { set_error("pitch %zu smaller than a row (%zu bytes)", pitch, row); return GOFPID_ERR_INVALID; }
+    FrameSlot &F = p->slots[p->frames % DEPTH];
+    if (!p->frames_pitch) {
+        p->frames_pitch = round_up(row, 128);
+        p->frames_stream = p->frames_pitch * p->H;
+    }
+    if (!F.d_frames) GOFPID_CUDA_TRY(cudaMalloc(&F.d_frames, p->frames_stream * p->n_streams));
+    cudaPointerAttributes attr;
+    bool pinned = false;
+    if (cudaPointerGetAttributes(&attr, h_frames) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
+    else cudaGetLastError();
+    const uint8_t *src = h_frames;
+    size_t spitch = pitch, sstride = stream_stride;
+    cudaStream_t sh = p->stream_h;
+    // stage A of the slot's previous frame must have finished reading the staging buffer
+    if (F.used) GOFPID_CUDA_TRY(cudaStreamWaitEvent(sh, F.ev_mask, 0));
+    if (!pinned) {
+        // pageable memory: stage through one pinned buffer (synchronous for the caller)
+        if (!p->h_frames) GOFPID_CUDA_TRY(cudaMallocHost(&p->h_frames, row * p->H * p->n_streams));
+        GOFPID_CUDA_TRY(cudaStreamSynchronize(sh)); // the previous copy out of h_frames is done
+        for (int z = 0; z < p->n_streams; z++)
+            for (int y = 0; y < p->H; y++)
+                memcpy(p->h_frames + ((size_t)z * p->H + y) * row, h_frames + z * stream_stride + (size_t)y * pitch, row);
+        src = p->h_frames; spitch = row; sstride = row * p->H;
+    }
+    if (sstride == spitch * p->H || p->n_streams == 1) {
+        GOFPID_CUDA_TRY(cudaMemcpy2DAsync(F.d_frames, p->frames_pitch, src, spitch, row,
+                                          (size_t)p->H * p->n_streams, cudaMemcpyHostToDevice, sh));
+    } else {
+        for (int z = 0; z < p->n_streams; z++)
+            GOFPID_CUDA_TRY(cudaMemcpy2DAsync(F.d_frames + z * p->frames_stream, p->frames_pitch,
+                                              src + z * sstride, spitch, row, p->H, cudaMemcpyHostToDevice, sh));
+    }
+    GOFPID_CUDA_TRY(cudaEventRecord(F.ev_h2d, sh));
+    GOFPID_CUDA_TRY(cudaStreamWaitEvent(p->stream, F.ev_h2d, 0));
+    return run_step(p, F.d_frames, p->frames_pitch, p->frames_stream, p->stream);
 }
 
 } // namespace
@@ -560,42 +669,30 @@ GOFPID_API int gofpid_pipeline_process_device(gofpid_pipeline *p, const uint8_t 
     return run_step(p, d_frames, pitch, stream_stride, (cudaStream_t)stream);
 }
 
+GOFPID_API int gofpid_pipeline_submit_host(gofpid_pipeline *p, const uint8_t *h_frames, size_t pitch,
+                                           size_t stream_stride)
+{
+    GOFPID_GUARD(p);
+    if (!h_frames) { set_error("null frame pointer"); return GOFPID_ERR_INVALID; }
+    return submit_host(p, h_frames, pitch, stream_stride);
+}
+
 GOFPID_API int gofpid_pipeline_process_host(gofpid_pipeline *p, const uint8_t *h_frames,
                                             size_t pitch, size_t stream_stride)
 {
     GOFPID_GUARD(p);
     if (!h_frames) { set_error("null frame pointer"); return GOFPID_ERR_INVALID; }
-    const size_t row = (size_t)p->W * p->C;
-    if (pitch < row) { set_error("pitch %zu smaller than a row (%zu bytes)", pitch, row); return GOFPID_ERR_INVALID; }
-    if (!p->d_frames) {
-        p->frames_pitch = round_up(row, 128);
-        p->frames_stream = p->frames_pitch * p->H;
-        GOFPID_CUDA_TRY(cudaMalloc(&p->d_frames, p->frames_stream * p->n_streams));
-    }
-    cudaPointerAttributes attr;
-    bool pinned = false;
-    if (cudaPointerGetAttributes(&attr, h_frames) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
-    else cudaGetLastError();
-    const uint8_t *src = h_frames;
-    size_t spitch = pitch, sstride = stream_stride;
-    if (!pinned) {
-        if (!p->h_frames) GOFPID_CUDA_TRY(cudaMallocHost(&p->h_frames, row * p->H * p->n_streams));
-        for (int z = 0; z < p->n_streams; z++)
-            for (int y = 0; y < p->H; y++)
-                memcpy(p->h_frames + ((size_t)z * p->H + y) * row, h_frames + z * stream_stride + (size_t)y * pitch, row);
-        src = p->h_frames; spitch = row; sstride = row * p->H;
-    }
-    if (sstride == spitch * p->H || p->n_streams == 1) {
-        GOFPID_CUDA_TRY(cudaMemcpy2DAsync(p->d_frames, p->frames_pitch, src, spitch, row,
-                                          (size_t)p->H * p->n_streams, cudaMemcpyHostToDevice, p->stream));
-    } else {
-        for (int z = 0; z < p->n_streams; z++)
-            GOFPID_CUDA_TRY(cudaMemcpy2DAsync(p->d_frames + z * p->frames_stream, p->frames_pitch,
-                                              src + z * sstride, spitch, row, p->H,
-                                              cudaMemcpyHostToDevice, p->stream));
-    }
-    GOFPID_TRY(run_step(p, p->d_frames, p->frames_pitch, p->frames_stream, p->stream));
-    return fetch_results(p);
+    GOFPID_TRY(submit_host(p, h_frames, pitch, stream_stride));
+    return fetch_results(p, selected_slot(p));
+}
+
+GOFPID_API int gofpid_pipeline_select(gofpid_pipeline *p, int age)
+{
+    GOFPID_GUARD(p);
+    if (age < 0 || age >= DEPTH) { set_error("age must be 0 (newest frame) or 1 (the one before)"); return GOFPID_ERR_INVALID; }
+    if (p->frames - 1 - age < 0) { set_error("no such frame yet"); return GOFPID_ERR_INVALID; }
+    p->selected = age;
+    return GOFPID_OK;
 }
 
 GOFPID_API int gofpid_pipeline_frame_info(gofpid_pipeline *p, int stream_idx, gofpid_frame_info *h_info)
@@ -603,8 +700,9 @@ GOFPID_API int gofpid_pipeline_frame_info(gofpid_pipeline *p, int stream_idx, go
     GOFPID_GUARD(p);
     GOFPID_TRY(check_stream_index(p, stream_idx));
     if (!h_info) { set_error("null output"); return GOFPID_ERR_INVALID; }
-    GOFPID_TRY(fetch_results(p));
-    *h_info = p->h_info[stream_idx];
+    FrameSlot *F = selected_slot(p);
+    GOFPID_TRY(fetch_results(p, F));
+    *h_info = F->h_info[stream_idx];
     return GOFPID_OK;
 }
 
@@ -615,11 +713,13 @@ GOFPID_API int gofpid_pipeline_blobs(gofpid_pipeline *p, int stream_idx, gofpid_
     GOFPID_GUARD(p);
     GOFPID_TRY(check_stream_index(p, stream_idx));
     if (!p->cfg.find_blobs) { set_error("pipeline was created with find_blobs = 0"); return GOFPID_ERR_INVALID; }
-    GOFPID_TRY(fetch_results(p));
-    const gofpid_frame_info &fi = p->h_info[stream_idx];
-    const int nk = std::min(fi.n_kept, p->blobs.max_kept);
-    const gofpid_blob *kb = p->h_kept + (size_t)stream_idx * p->blobs.max_kept;
-    const int32_t *pts = p->h_points + (size_t)stream_idx * p->blobs.max_points * 2;
+    FrameSlot *F = selected_slot(p);
+    GOFPID_TRY(fetch_results(p, F));
+    const BlobBuffers &B = F->blobs;
+    const gofpid_frame_info &fi = F->h_info[stream_idx];
+    const int nk = std::min(fi.n_kept, B.max_kept);
+    const gofpid_blob *kb = F->h_kept + (size_t)stream_idx * B.max_kept;
+    const int32_t *pts = F->h_points + (size_t)stream_idx * B.max_points * 2;
     // the reference's order: descending raster order of each component's first pixel
     std::vector<int> order(nk);
     for (int i = 0; i < nk; i++) order[i] = i;
@@ -630,8 +730,7 @@ GOFPID_API int gofpid_pipeline_blobs(gofpid_pipeline *p, int stream_idx, gofpid_
     if (n_points) *n_points = total;
     if (fi.overflow) {
         set_error("blob capacity exceeded (flags %d): components %d/%d, kept %d/%d, points %d/%d",
-                  fi.overflow, fi.n_components, p->blobs.max_blobs, fi.n_kept, p->blobs.max_kept,
-                  fi.n_points, p->blobs.max_points);
+                  fi.overflow, fi.n_components, B.max_blobs, fi.n_kept, B.max_kept, fi.n_points, B.max_points);
         return GOFPID_ERR_OVERFLOW;
     }
     if (!h_blobs && !h_points) return GOFPID_OK; // size query
@@ -656,12 +755,14 @@ GOFPID_API int gofpid_pipeline_mask(gofpid_pipeline *p, int stream_idx, uint8_t 
     GOFPID_GUARD(p);
     GOFPID_TRY(check_stream_index(p, stream_idx));
     if (!dst || dst_pitch < (size_t)p->W) { set_error("bad destination"); return GOFPID_ERR_INVALID; }
-    if (!p->stepped) { set_error("no frame has been processed yet"); return GOFPID_ERR_INVALID; }
-    const uint8_t *src = p->d_mask[p->final_mask] + (size_t)stream_idx * p->mask_stream;
+    FrameSlot *F = selected_slot(p);
+    if (!F) { set_error("no frame has been processed yet"); return GOFPID_ERR_INVALID; }
+    GOFPID_CUDA_TRY(cudaEventSynchronize(F->ev_mask));
+    const uint8_t *src = F->d_final + (size_t)stream_idx * p->mask_stream;
     GOFPID_CUDA_TRY(cudaMemcpy2DAsync(dst, dst_pitch, src, p->mask_pitch, p->W, p->H,
                                       dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,
-                                      p->last_stream));
-    GOFPID_CUDA_TRY(cudaStreamSynchronize(p->last_stream));
+                                      p->stream_c));
+    GOFPID_CUDA_TRY(cudaStreamSynchronize(p->stream_c));
     return GOFPID_OK;
 }
 
@@ -672,8 +773,10 @@ GOFPID_API int gofpid_pipeline_labels(gofpid_pipeline *p, int stream_idx, int32_
     GOFPID_TRY(check_stream_index(p, stream_idx));
     if (!p->cfg.find_blobs) { set_error("pipeline was created with find_blobs = 0"); return GOFPID_ERR_INVALID; }
     if (!dst || dst_pitch < (size_t)p->W * sizeof(int32_t) || dst_pitch % sizeof(int32_t)) { set_error("bad destination"); return GOFPID_ERR_INVALID; }
-    if (!p->stepped) { set_error("no frame has been processed yet"); return GOFPID_ERR_INVALID; }
-    cudaStream_t s = p->last_stream;
+    FrameSlot *F = selected_slot(p);
+    if (!F) { set_error("no frame has been processed yet"); return GOFPID_ERR_INVALID; }
+    GOFPID_CUDA_TRY(cudaEventSynchronize(F->ev_blobs));
+    cudaStream_t s = p->stream_c;
     int32_t *tmp = nullptr;
     int32_t *out = dst;
     size_t out_pitch = dst_pitch / sizeof(int32_t);
@@ -681,9 +784,10 @@ GOFPID_API int gofpid_pipeline_labels(gofpid_pipeline *p, int stream_idx, int32_
         GOFPID_CUDA_TRY(cudaMalloc(&tmp, (size_t)p->W * p->H * sizeof(int32_t)));
         out = tmp; out_pitch = p->W;
     }
-    int rc = launch_canonical_labels(p->d_mask[p->final_mask] + (size_t)stream_idx * p->mask_stream,
-                                     p->mask_pitch, p->blobs.labels + (size_t)stream_idx * p->blobs.labels_stream,
-                                     p->blobs.labels_pitch, out, out_pitch, p->H, p->W, s);
+    const BlobBuffers &B = F->blobs;
+    int rc = launch_canonical_labels(F->d_final + (size_t)stream_idx * p->mask_stream, p->mask_pitch,
+                                     B.labels + (size_t)stream_idx * B.labels_stream, B.labels_pitch, out,
+                                     out_pitch, p->H, p->W, s);
     if (rc == GOFPID_OK && !dst_is_device) {
         if (cudaMemcpy2DAsync(dst, dst_pitch, tmp, (size_t)p->W * sizeof(int32_t), (size_t)p->W * sizeof(int32_t),
                               p->H, cudaMemcpyDeviceToHost, s) != cudaSuccess) { set_error("label copy failed"); rc = GOFPID_ERR_CUDA; }
@@ -699,17 +803,19 @@ GOFPID_API int gofpid_pipeline_components(gofpid_pipeline *p, int stream_idx, in
     GOFPID_GUARD(p);
     GOFPID_TRY(check_stream_index(p, stream_idx));
     if (!p->cfg.find_blobs) { set_error("pipeline was created with find_blobs = 0"); return GOFPID_ERR_INVALID; }
-    GOFPID_TRY(fetch_results(p));
-    const gofpid_frame_info &fi = p->h_info[stream_idx];
-    const int n = std::min(fi.n_components, p->blobs.max_blobs);
+    FrameSlot *F = selected_slot(p);
+    GOFPID_TRY(fetch_results(p, F));
+    const BlobBuffers &B = F->blobs;
+    const gofpid_frame_info &fi = F->h_info[stream_idx];
+    const int n = std::min(fi.n_components, B.max_blobs);
     if (n_components) *n_components = fi.n_components;
     if (!h_stats) return GOFPID_OK;
     if (n > capacity) { set_error("output capacity too small: need %d components", n); return GOFPID_ERR_INVALID; }
     std::vector<int32_t> rec((size_t)n * 8);
     if (n > 0)
-        GOFPID_CUDA_TRY(cudaMemcpy(rec.data(), p->blobs.comp + (size_t)stream_idx * p->blobs.max_blobs * 8,
+        GOFPID_CUDA_TRY(cudaMemcpy(rec.data(), B.comp + (size_t)stream_idx * B.max_blobs * 8,
                                    rec.size() * sizeof(int32_t), cudaMemcpyDeviceToHost));
-    const int LP = (int)p->blobs.labels_pitch;
+    const int LP = (int)B.labels_pitch;
     for (int i = 0; i < n; i++) {
         const int32_t *r = &rec[(size_t)i * 8];
         const int fy = r[0] / LP, fx = r[0] - fy * LP;
@@ -829,7 +935,7 @@ GOFPID_API int gofpid_pipeline_stage_ms(gofpid_pipeline *p, float *h_ms5)
 {
     GOFPID_GUARD(p);
     if (!h_ms5) { set_error("null output"); return GOFPID_ERR_INVALID; }
-    if (!p->profiling || !p->stepped) { set_error("profiling is off or no frame processed"); return GOFPID_ERR_INVALID; }
+    if (!p->profiling || p->frames == 0) { set_error("profiling is off or no frame processed"); return GOFPID_ERR_INVALID; }
     GOFPID_CUDA_TRY(cudaEventSynchronize(p->ev[3]));
     float blobs_ms = 0.f;
     GOFPID_CUDA_TRY(cudaEventElapsedTime(&h_ms5[0], p->ev[4], p->ev[1]));

@@ -149,6 +149,15 @@ class HotPath:
         """process() for a raw host pointer (e.g. a pinned torch tensor's data_ptr())."""
         nat.check(self._L.gofpid_pipeline_process_host(self._h, ptr, pitch, stream_stride))
 
+    def submit_pinned(self, ptr, pitch, stream_stride):
+        """Asynchronous process_pinned(): enqueue the H2D copy and the step, return at once.
+        Up to two frames are in flight; collect results with select(1) + the getters."""
+        nat.check(self._L.gofpid_pipeline_submit_host(self._h, ptr, pitch, stream_stride))
+
+    def select(self, age=0):
+        """Result getters refer to the newest frame (age 0) or the one before it (age 1)."""
+        nat.check(self._L.gofpid_pipeline_select(self._h, age))
+
     def process_device(self, ptr, pitch, stream_stride, cuda_stream=0):
         """One time step from frames already resident in HBM; asynchronous on `cuda_stream`."""
         nat.check(self._L.gofpid_pipeline_process_device(self._h, ptr, pitch, stream_stride,
