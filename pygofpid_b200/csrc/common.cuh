@@ -98,12 +98,16 @@ struct Mog2Params {
     int detectShadows, shadowVal, history;
     float ct;
 };
+// MOG2 model, tiled: per stream tiles_x * tiles_y tiles of MOG2_TILE_W x MOG2_TILE_H pixels; a
+// tile is one contiguous block [mode][plane: weight, var, mean c..][512 px] of floats, so its
+// live modes are a single run of bytes for the bulk-copy engine.
+constexpr int MOG2_TILE_W = 64;
+constexpr int MOG2_TILE_H = 8;
 struct Mog2Model {
-    float *planes;        // per stream: weight[5], var[5], mean[5][C] planes of PW*H floats
-    uint8_t *nmodes;      // per stream: PW*H bytes
-    size_t plane_elems;   // PW*H
-    size_t stream_planes; // planes per stream = 10 + 5*C
-    int PW;               // row pitch in elements (multiple of 32)
+    float *planes;      // [stream][tile][5][2 + C][512]
+    uint8_t *nmodes;    // [stream][tile][512]
+    uint8_t *tile_nmax; // [stream][tile]: most live modes of any pixel of the tile
+    int tiles_x, tiles_y;
 };
 struct KnnParams {
     float Tb, tau;

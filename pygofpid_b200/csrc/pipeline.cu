@@ -165,7 +165,9 @@ int reset_state(gofpid_pipeline *p)
     t.knn_rng = p->cfg.knn_rng_seed ? p->cfg.knn_rng_seed : 0xffffffffULL;
     GOFPID_CUDA_TRY(cudaMemcpy(p->d_tick, &t, sizeof(t), cudaMemcpyHostToDevice));
     if (p->cfg.detector == GOFPID_DETECT_MOG2) {
-        GOFPID_CUDA_TRY(cudaMemset(p->mog2.nmodes, 0, p->mog2.plane_elems * p->n_streams));
+        const size_t nt = (size_t)p->mog2.tiles_x * p->mog2.tiles_y * p->n_streams;
+        GOFPID_CUDA_TRY(cudaMemset(p->mog2.nmodes, 0, nt * MOG2_TILE_W * MOG2_TILE_H));
+        GOFPID_CUDA_TRY(cudaMemset(p->mog2.tile_nmax, 0, nt));
     } else if (p->cfg.detector == GOFPID_DETECT_KNN) {
         const size_t pe = p->knn.plane_elems;
         GOFPID_CUDA_TRY(cudaMemset(p->knn.samples, 0, pe * 21 * (p->C + 1) * p->n_streams));
@@ -182,7 +184,7 @@ void free_all(gofpid_pipeline *p)
 {
     cudaFree(p->d_tick);
     cudaFree(p->d_mask_det);
-    cudaFree(p->mog2.planes); cudaFree(p->mog2.nmodes);
+    cudaFree(p->mog2.planes); cudaFree(p->mog2.nmodes); cudaFree(p->mog2.tile_nmax);
     cudaFree(p->knn.samples); cudaFree(p->knn.nxt); cudaFree(p->knn.idx); cudaFree(p->knn.fresh);
     cudaFree(p->fd.prev);
     cudaFree(p->d_knn_table); cudaFree(p->d_pow2tab);
@@ -225,7 +227,8 @@ int build(gofpid_pipeline *p)
 
     const int PW = (int)round_up((size_t)W, 32);
     const size_t pe = (size_t)PW * H;
-    p->mog2.PW = PW; p->mog2.plane_elems = pe; p->mog2.stream_planes = 10 + 5 * C;
+    p->mog2.tiles_x = (W + MOG2_TILE_W - 1) / MOG2_TILE_W;
+    p->mog2.tiles_y = (H + MOG2_TILE_H - 1) / MOG2_TILE_H;
     p->knn.PW = PW; p->knn.plane_elems = pe;
     Mog2Params &mp = p->mog2p;
     mp.Tb = cfg.mog2_var_threshold; mp.TB = cfg.mog2_background_ratio; mp.Tg = cfg.mog2_var_threshold_gen;
@@ -238,8 +241,11 @@ int build(gofpid_pipeline *p)
 
     if (cfg.detector == GOFPID_DETECT_MOG2) {
         if (cfg.mog2_history < 1) { set_error("MOG2 history must be >= 1"); return GOFPID_ERR_INVALID; }
-        GOFPID_TRY(alloc_zero((void **)&p->mog2.planes, pe * p->mog2.stream_planes * sizeof(float) * S));
-        GOFPID_TRY(alloc_zero((void **)&p->mog2.nmodes, pe * S));
+        const size_t nt = (size_t)p->mog2.tiles_x * p->mog2.tiles_y * S;
+        const size_t tpx = (size_t)MOG2_TILE_W * MOG2_TILE_H;
+        GOFPID_TRY(alloc_zero((void **)&p->mog2.planes, nt * GOFPID_MOG2_NMIX * (2 + C) * tpx * sizeof(float)));
+        GOFPID_TRY(alloc_zero((void **)&p->mog2.nmodes, nt * tpx));
+        GOFPID_TRY(alloc_zero((void **)&p->mog2.tile_nmax, nt));
     } else if (cfg.detector == GOFPID_DETECT_KNN) {
         if (cfg.knn_history < 1) { set_error("KNN history must be >= 1"); return GOFPID_ERR_INVALID; }
         GOFPID_TRY(alloc_zero((void **)&p->knn.samples, pe * 21 * (C + 1) * S));
@@ -833,22 +839,27 @@ GOFPID_API int gofpid_pipeline_mog2_model(gofpid_pipeline *p, int stream_idx, fl
     GOFPID_TRY(check_stream_index(p, stream_idx));
     if (p->cfg.detector != GOFPID_DETECT_MOG2) { set_error("detector is not MOG2"); return GOFPID_ERR_INVALID; }
     GOFPID_CUDA_TRY(cudaDeviceSynchronize());
-    const int H = p->H, W = p->W, C = p->C, PW = p->mog2.PW;
-    const size_t pe = p->mog2.plane_elems, np = p->mog2.stream_planes;
-    std::vector<float> planes(pe * np);
-    std::vector<uint8_t> nm(pe);
-    GOFPID_CUDA_TRY(cudaMemcpy(planes.data(), p->mog2.planes + (size_t)stream_idx * np * pe,
-                               planes.size() * sizeof(float), cudaMemcpyDeviceToHost));
-    GOFPID_CUDA_TRY(cudaMemcpy(nm.data(), p->mog2.nmodes + (size_t)stream_idx * pe, pe, cudaMemcpyDeviceToHost));
+    const int H = p->H, W = p->W, C = p->C;
+    const size_t nt = (size_t)p->mog2.tiles_x * p->mog2.tiles_y, tpx = (size_t)MOG2_TILE_W * MOG2_TILE_H;
+    const size_t tile_floats = (size_t)GOFPID_MOG2_NMIX * (2 + C) * tpx;
+    std::vector<float> tiles(nt * tile_floats);
+    std::vector<uint8_t> nm(nt * tpx);
+    GOFPID_CUDA_TRY(cudaMemcpy(tiles.data(), p->mog2.planes + (size_t)stream_idx * nt * tile_floats,
+                               tiles.size() * sizeof(float), cudaMemcpyDeviceToHost));
+    GOFPID_CUDA_TRY(cudaMemcpy(nm.data(), p->mog2.nmodes + (size_t)stream_idx * nt * tpx, nm.size(),
+                               cudaMemcpyDeviceToHost));
     for (int y = 0; y < H; y++)
         for (int x = 0; x < W; x++) {
-            const size_t s = (size_t)y * PW + x, d = (size_t)y * W + x;
-            if (h_nmodes) h_nmodes[d] = nm[s];
-            for (int k = 0; k < 5; k++) {
-                if (h_weight) h_weight[d * 5 + k] = planes[(size_t)k * pe + s];
-                if (h_var) h_var[d * 5 + k] = planes[(size_t)(5 + k) * pe + s];
+            const size_t t = (size_t)(y / MOG2_TILE_H) * p->mog2.tiles_x + x / MOG2_TILE_W;
+            const size_t l = (size_t)(y % MOG2_TILE_H) * MOG2_TILE_W + x % MOG2_TILE_W;
+            const size_t d = (size_t)y * W + x;
+            if (h_nmodes) h_nmodes[d] = nm[t * tpx + l];
+            for (int k = 0; k < GOFPID_MOG2_NMIX; k++) {
+                const float *mk = &tiles[t * tile_floats + (size_t)k * (2 + C) * tpx];
+                if (h_weight) h_weight[d * 5 + k] = mk[l];
+                if (h_var) h_var[d * 5 + k] = mk[tpx + l];
                 if (h_mean)
-                    for (int c = 0; c < C; c++) h_mean[(d * 5 + k) * C + c] = planes[(size_t)(10 + k * C + c) * pe + s];
+                    for (int c = 0; c < C; c++) h_mean[(d * 5 + k) * C + c] = mk[(2 + c) * tpx + l];
             }
         }
     return GOFPID_OK;
@@ -913,13 +924,16 @@ GOFPID_API int gofpid_pipeline_mog2_mean_modes(gofpid_pipeline *p, double *mean_
     if (p->cfg.detector != GOFPID_DETECT_MOG2) { set_error("detector is not MOG2"); return GOFPID_ERR_INVALID; }
     if (!mean_modes) { set_error("null output"); return GOFPID_ERR_INVALID; }
     GOFPID_CUDA_TRY(cudaDeviceSynchronize());
-    const size_t pe = p->mog2.plane_elems;
-    std::vector<uint8_t> nm(pe * p->n_streams);
+    const size_t nt = (size_t)p->mog2.tiles_x * p->mog2.tiles_y, tpx = (size_t)MOG2_TILE_W * MOG2_TILE_H;
+    std::vector<uint8_t> nm(nt * tpx * p->n_streams);
     GOFPID_CUDA_TRY(cudaMemcpy(nm.data(), p->mog2.nmodes, nm.size(), cudaMemcpyDeviceToHost));
     double sum = 0;
     for (int z = 0; z < p->n_streams; z++)
         for (int y = 0; y < p->H; y++)
-            for (int x = 0; x < p->W; x++) sum += nm[(size_t)z * pe + (size_t)y * p->mog2.PW + x];
+            for (int x = 0; x < p->W; x++) {
+                const size_t t = (size_t)(y / MOG2_TILE_H) * p->mog2.tiles_x + x / MOG2_TILE_W;
+                sum += nm[((size_t)z * nt + t) * tpx + (size_t)(y % MOG2_TILE_H) * MOG2_TILE_W + x % MOG2_TILE_W];
+            }
     *mean_modes = sum / ((double)p->n_streams * p->H * p->W);
     return GOFPID_OK;
 }
