@@ -118,6 +118,8 @@ typedef struct gofpid_blob {
     int32_t area_px;            /* pixel count of the 8-connected component            */
     int32_t n_points;           /* contour length (CHAIN_APPROX_NONE)                  */
     int32_t point_offset;       /* index of the first point in the frame's point pool  */
+    int32_t nested;             /* device-side flag: enclosed by another blob (such    */
+    int32_t reserved;           /* blobs are removed before the list is returned)      */
     int64_t a00, a10, a01;      /* Green sums over the contour polygon (exact)         */
 } gofpid_blob;
 
@@ -125,11 +127,11 @@ typedef struct gofpid_blob {
 typedef struct gofpid_frame_info {
     int32_t n_components; /* 8-connected foreground components                         */
     int32_t n_candidates; /* external components passing the bbox pre-filter           */
-    int32_t n_kept;       /* blobs in the output list                                  */
+    int32_t n_kept;       /* contours with contourArea >= area_min (incl. enclosed ones, see reserved[0]) */
     int32_t n_points;     /* contour points in the pool                                */
     int32_t overflow;     /* bit0: components, bit1: kept blobs, bit2: points, bit3: internal */
     int32_t frame_index;  /* 1-based count of frames this stream has processed         */
-    int32_t reserved[2];
+    int32_t reserved[2];  /* [0]: how many of n_kept are enclosed by another blob (not returned)     */
 } gofpid_frame_info;
 
 typedef struct gofpid_pipeline gofpid_pipeline; /* opaque */

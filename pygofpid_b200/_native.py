@@ -53,7 +53,8 @@ class Config(ct.Structure):
 class Blob(ct.Structure):
     _fields_ = [("first", ct.c_int32), ("x0", ct.c_int32), ("y0", ct.c_int32), ("x1", ct.c_int32),
                 ("y1", ct.c_int32), ("area_px", ct.c_int32), ("n_points", ct.c_int32),
-                ("point_offset", ct.c_int32), ("a00", ct.c_int64), ("a10", ct.c_int64),
+                ("point_offset", ct.c_int32), ("nested", ct.c_int32), ("reserved", ct.c_int32),
+                ("a00", ct.c_int64), ("a10", ct.c_int64),
                 ("a01", ct.c_int64)]
 
 

@@ -123,7 +123,7 @@ label_tiles_kernel(ImageU8 mask, int32_t *labels, size_t LP, size_t labels_strea
     if (blockIdx.x == 0 && blockIdx.y == 0 && tx == 0 && ty == 0) {
         gofpid_frame_info *fi = info + blockIdx.z;
         fi->n_components = 0; fi->n_candidates = 0; fi->n_kept = 0; fi->n_points = 0;
-        fi->overflow = 0; fi->frame_index = tick ? tick->nframes : 0;
+        fi->overflow = 0; fi->frame_index = tick ? tick->nframes : 0; fi->reserved[0] = 0; fi->reserved[1] = 0;
     }
 
     uint32_t mw = 0;
@@ -138,53 +138,40 @@ label_tiles_kernel(ImageU8 mask, int32_t *labels, size_t LP, size_t labels_strea
     if ((tx & 7) == 0) Fw[ty][tx >> 3] = half;
     __syncthreads();
 
-    const int wvalid = min(CCL_TW, W - x0);                 // valid columns of this tile
-    const unsigned long long V = bits_below(wvalid);
+    // most tiles of a foreground mask are empty: nothing to label, nothing to write
+    if (!__syncthreads_or(nib != 0)) return;
+
     const bool row_ok = y < H;
     const unsigned long long F = ((unsigned long long)Fw[ty][1] << 32) | Fw[ty][0];
-    unsigned long long Fp = 0, Vp = 0;
-    if (ty > 0) { Fp = ((unsigned long long)Fw[ty - 1][1] << 32) | Fw[ty - 1][0]; Vp = V; }
+    const unsigned long long Fp = ty > 0 ? (((unsigned long long)Fw[ty - 1][1] << 32) | Fw[ty - 1][0]) : 0ULL;
 
-    // provisional labels: every pixel points at its run start; a background run that touches
-    // the frame border is the virtual OUTSIDE node (0).  The four pixels of a thread mostly
-    // share a run, so the 64-bit run searches are done once per run, not once per pixel.
-    int ra[4]; // run start column of each pixel (-1: outside the image)
+    // provisional labels: every foreground pixel points at the start of its horizontal run.  The
+    // four pixels of a thread mostly share a run, so the 64-bit run searches are done once per
+    // run, not once per pixel.
+    int ra[4]; // run start column of each foreground pixel (-1: background / outside)
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         const int c = lx + j;
         const int li = ty * CCL_TW + c;
-        if (!row_ok || c >= wvalid) { ra[j] = -1; lab[li] = li + 1; continue; }
-        const bool fg = (F >> c) & 1ULL;
-        const unsigned long long S = fg ? F : (~F & V);
-        int a;
-        if (j > 0 && ra[j - 1] >= 0 && (((F >> (c - 1)) & 1ULL) != 0) == fg) a = ra[j - 1];
-        else a = run_start(S, c);
+        if (!((nib >> j) & 1u)) { ra[j] = -1; lab[li] = li + 1; continue; }
+        const int a = (j > 0 && ra[j - 1] >= 0) ? ra[j - 1] : run_start(F, c);
         ra[j] = a;
-        int v = ty * CCL_TW + a + 1;
-        if (a == c && !fg) {
-            const int b = run_end(S, c);
-            if (y == 0 || y == H - 1 || x0 + a == 0 || x0 + b == W - 1) v = 0;
-        }
-        lab[li] = v;
+        lab[li] = ty * CCL_TW + a + 1;
     }
     __syncthreads();
 
-    // vertical unions, one thread per run
-    if (row_ok && ty > 0) {
+    // vertical unions (8-connectivity), one thread per run
+    if (row_ok && ty > 0 && Fp) {
 #pragma unroll
         for (int j = 0; j < 4; j++) {
             const int c = lx + j;
-            if (ra[j] != c) continue; // not a run start (or outside the image)
-            const bool fg = (F >> c) & 1ULL;
-            const unsigned long long S = fg ? F : (~F & V);
-            const int b = run_end(S, c);
-            const unsigned long long Sp = fg ? Fp : (~Fp & Vp);
-            const int lo = fg ? max(c - 1, 0) : c, hi = fg ? min(b + 1, 63) : b;
-            unsigned long long m = Sp & bits_below(hi + 1) & ~bits_below(lo);
+            if (ra[j] != c) continue; // not a run start
+            const int b = run_end(F, c);
+            unsigned long long m = Fp & bits_below(min(b + 1, 63) + 1) & ~bits_below(max(c - 1, 0));
             const int me = ty * CCL_TW + c + 1;
             while (m) {
                 const int pos = __ffsll((long long)m) - 1;
-                const int ap = run_start(Sp, pos), bp = run_end(Sp, pos);
+                const int ap = run_start(Fp, pos), bp = run_end(Fp, pos);
                 uf_union_s(lab, me, (ty - 1) * CCL_TW + ap + 1);
                 m &= ~bits_below(bp + 1);
             }
@@ -206,14 +193,14 @@ label_tiles_kernel(ImageU8 mask, int32_t *labels, size_t LP, size_t labels_strea
         if (rr[j] >= 0) lab[ty * CCL_TW + lx + j] = rr[j];
     __syncthreads();
 
-    if (y >= H || x >= W) return;
+    if (!nib) return; // background entries of the label image are never read
     int out[4];
 #pragma unroll
     for (int j = 0; j < 4; j++) {
         if (ra[j] < 0) { out[j] = 0; continue; }
         if (j > 0 && ra[j] == ra[j - 1]) { out[j] = out[j - 1]; continue; }
-        const int r = lab[ty * CCL_TW + ra[j]]; // root of the run start (0 = OUTSIDE)
-        out[j] = r == 0 ? 0 : (int)((size_t)(y0 + (r - 1) / CCL_TW) * LP + x0 + (r - 1) % CCL_TW) + 1;
+        const int r = lab[ty * CCL_TW + ra[j]]; // root of the run start
+        out[j] = (int)((size_t)(y0 + (r - 1) / CCL_TW) * LP + x0 + (r - 1) % CCL_TW) + 1;
     }
     int32_t *lrow = labels + (size_t)blockIdx.z * labels_stream + (size_t)y * LP;
     *reinterpret_cast<int4 *>(lrow + x) = make_int4(out[0], out[1], out[2], out[3]);
@@ -239,13 +226,13 @@ merge_tiles_kernel(ImageU8 mask, int32_t *labels, size_t LP, size_t labels_strea
         if (yy < 0 || xx < 0 || xx >= W) return 2;
         return m[(size_t)yy * mask.pitch + xx] != 0 ? 1 : 0;
     };
-    const int c = cl(y, x);
+    if (cl(y, x) != 1) return; // only foreground is labelled
     const int v = (int)((size_t)y * LP + x) + 1;
     const bool top = y == y0, left = x == x0, right = x == x0 + CCL_TW - 1;
     const int cw = cl(y, x - 1), cn = cl(y - 1, x);
-    if (left && cw == c) uf_union_g(lab, v, v - 1);
-    if (top && cn == c) uf_union_g(lab, v, v - (int)LP);
-    if (c == 1 && cn != 1) {
+    if (left && cw == 1) uf_union_g(lab, v, v - 1);
+    if (top && cn == 1) uf_union_g(lab, v, v - (int)LP);
+    if (cn != 1) {
         if ((top || left) && cw != 1 && cl(y - 1, x - 1) == 1) uf_union_g(lab, v, v - (int)LP - 1);
         if ((top || right) && cl(y - 1, x + 1) == 1) uf_union_g(lab, v, v - (int)LP + 1);
     }
@@ -265,21 +252,20 @@ flatten_kernel(ImageU8 mask, int32_t *labels, size_t LP, size_t labels_stream, i
     const uint8_t *mrow = mask.base + (size_t)blockIdx.z * mask.stream_stride + (size_t)y * mask.pitch;
     uint32_t mw = 0;
     int v[4] = {0, 0, 0, 0};
-    if (x < W) {
-        mw = *reinterpret_cast<const uint32_t *>(mrow + x);
+    if (x < W) mw = *reinterpret_cast<const uint32_t *>(mrow + x);
+    if (mw) { // label entries exist for foreground pixels only
         const int4 v4 = *reinterpret_cast<const int4 *>(lab + (size_t)y * LP + x);
         v[0] = v4.x; v[1] = v4.y; v[2] = v4.z; v[3] = v4.w;
     }
     unsigned nib = 0;
 #pragma unroll
     for (int j = 0; j < 4; j++) {
-        if (x + j >= W) continue;
-        const bool fg = ((mw >> (8 * j)) & 255) != 0;
-        if (fg) nib |= 1u << j;
+        if (x + j >= W || ((mw >> (8 * j)) & 255) == 0) { v[j] = 0; continue; }
+        nib |= 1u << j;
         const int self = (int)((size_t)y * LP + x + j) + 1;
         const int r = uf_find_g(lab, v[j]);
         v[j] = r;
-        if (r == self && fg) {
+        if (r == self) {
             gofpid_frame_info *fi = info + blockIdx.z;
             const int s = atomicAdd(&fi->n_components, 1);
             int32_t *sl = slot + (size_t)blockIdx.z * LP * H;
@@ -302,7 +288,7 @@ flatten_kernel(ImageU8 mask, int32_t *labels, size_t LP, size_t labels_stream, i
         bitimg[(size_t)blockIdx.z * bit_stream + (size_t)(y + 1) * bit_pitch + 1 + (x >> 5)] = word;
     // roots are final here (merging finished with the previous kernel), so writing the root
     // over a non-root entry only shortens paths other threads may still be walking
-    if (x < W) *reinterpret_cast<int4 *>(lab + (size_t)y * LP + x) = make_int4(v[0], v[1], v[2], v[3]);
+    if (nib) *reinterpret_cast<int4 *>(lab + (size_t)y * LP + x) = make_int4(v[0], v[1], v[2], v[3]);
 }
 
 // ------------------------------------------------------------------------------------
@@ -322,8 +308,10 @@ stats_kernel(ImageU8 mask, const int32_t *labels, size_t LP, size_t labels_strea
     if (inside) {
         mw = *reinterpret_cast<const uint32_t *>(mask.base + (size_t)blockIdx.z * mask.stream_stride +
                                                  (size_t)y * mask.pitch + x);
-        const int4 v4 = *reinterpret_cast<const int4 *>(lab + (size_t)y * LP + x);
-        v[0] = v4.x; v[1] = v4.y; v[2] = v4.z; v[3] = v4.w;
+        if (mw) {
+            const int4 v4 = *reinterpret_cast<const int4 *>(lab + (size_t)y * LP + x);
+            v[0] = v4.x; v[1] = v4.y; v[2] = v4.z; v[3] = v4.w;
+        }
     }
     // runs of equal component inside the thread's four pixels, flushed warp-aggregated
     int cur = -1, cnt = 0, rx0 = 0, rx1 = 0;
@@ -500,8 +488,6 @@ trace_kernel(const int32_t *labels, size_t LP, size_t labels_stream, const int32
         const int bw = bx1 - bx0 + 1, bh = by1 - by0 + 1;
         // cv.contourArea <= (w-1)(h-1): skip boxes that cannot reach area_min
         if ((double)(bw - 1) * (double)(bh - 1) < area_min) continue;
-        // RETR_EXTERNAL: the background left of the first pixel must reach the frame border
-        if (xs > 0 && lab[first - 1] != 0) continue;
         if (tid == 0) atomicAdd(&fi->n_candidates, 1);
 #ifdef GOFPID_TRACE_DEBUG
         long long dbg_t[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -526,7 +512,7 @@ trace_kernel(const int32_t *labels, size_t LP, size_t labels_stream, const int32
                 if (keep >= 0) {
                     gofpid_blob *kb = kept + (size_t)z * max_kept + keep;
                     kb->first = ys * W + xs; kb->x0 = bx0; kb->y0 = by0; kb->x1 = bx1; kb->y1 = by1;
-                    kb->area_px = cr[CR_AREA]; kb->n_points = 1; kb->point_offset = off;
+                    kb->area_px = cr[CR_AREA]; kb->n_points = 1; kb->point_offset = off; kb->nested = 0; kb->reserved = 0;
                     kb->a00 = 0; kb->a10 = 0; kb->a01 = 0;
                     int32_t *dst = points + ((size_t)z * max_points + off) * 2;
                     dst[0] = xs; dst[1] = ys;
@@ -724,7 +710,7 @@ trace_kernel(const int32_t *labels, size_t LP, size_t labels_stream, const int32
                         kb->first = ys * W + xs;
                         kb->x0 = bx0; kb->y0 = by0; kb->x1 = bx1; kb->y1 = by1;
                         kb->area_px = cr[CR_AREA];
-                        kb->n_points = npts; kb->point_offset = base;
+                        kb->n_points = npts; kb->point_offset = base; kb->nested = 0; kb->reserved = 0;
                         kb->a00 = t00; kb->a10 = 0; kb->a01 = 0;
                         if (npts == 0) keep = -1;
                     }
@@ -793,6 +779,55 @@ extern "C" __attribute__((visibility("default"))) int gofpid_debug_trace_dump(lo
 #endif
 
 // ------------------------------------------------------------------------------------
+// 6. RETR_EXTERNAL: drop blobs that lie inside a hole of another blob
+// ------------------------------------------------------------------------------------
+// cv.findContours(RETR_EXTERNAL) returns only components that are not enclosed by another
+// component's outer border.  A blob k is enclosed iff some blob j has a strictly larger box and
+// k's first pixel lies inside j's outer contour polygon (even-odd crossing count of the ray to
+// +x; contour edges are unit steps, so an edge crosses the ray exactly at its endpoint with
+// y == fy).  Enclosing blobs are at least as large as what they enclose, so testing the kept
+// blobs against each other is enough.  One warp per blob.
+__global__ void __launch_bounds__(256)
+nest_kernel(gofpid_frame_info *info, gofpid_blob *kept, const int32_t *points, int max_kept, int max_points,
+            int W)
+{
+    const int z = blockIdx.x;
+    gofpid_frame_info *fi = info + z;
+    const int nk = min(fi->n_kept, max_kept);
+    gofpid_blob *kb = kept + (size_t)z * max_kept;
+    const int32_t *pts = points + (size_t)z * max_points * 2;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int k = warp; k < nk; k += nwarps) {
+        const gofpid_blob bk = kb[k];
+        const int fy = bk.first / W, fx = bk.first - fy * W;
+        bool nested = false;
+        for (int j = 0; j < nk && !nested; j++) {
+            if (j == k) continue;
+            const gofpid_blob bj = kb[j];
+            if (!(bj.x0 < bk.x0 && bj.y0 < bk.y0 && bj.x1 > bk.x1 && bj.y1 > bk.y1)) continue;
+            if (bj.n_points <= 0) continue;
+            const int32_t *cj = pts + (size_t)bj.point_offset * 2;
+            unsigned crossings = 0;
+            for (int i = lane; i < bj.n_points; i += 32) {
+                const int i2 = i + 1 == bj.n_points ? 0 : i + 1;
+                const int xa = cj[2 * i], ya = cj[2 * i + 1], xb = cj[2 * i2], yb = cj[2 * i2 + 1];
+                if ((ya > fy) != (yb > fy)) {
+                    const int xe = ya == fy ? xa : xb; // the endpoint on the ray's row
+                    if (fx < xe) crossings++;
+                }
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) crossings += __shfl_xor_sync(0xffffffffu, crossings, o);
+            nested = crossings & 1u;
+        }
+        if (lane == 0 && nested) {
+            kb[k].nested = 1;
+            atomicAdd(&fi->reserved[0], 1);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------
 static int launch_labelling(ImageU8 mask, int32_t *labels, size_t LP, size_t labels_stream, int H,
@@ -828,7 +863,9 @@ int launch_blobs(const BlobBuffers &B, ImageU8 mask, int H, int W, int n_streams
         B.labels, B.labels_pitch, B.labels_stream, B.comp, B.info, B.kept, B.points, B.max_blobs,
         B.max_kept, B.max_points, B.area_min, B.bitimg, B.bit_pitch, B.bit_stream, H, W);
     GOFPID_CUDA_TRY(cudaGetLastError());
-    if (n_launches) *n_launches = 5;
+    nest_kernel<<<n_streams, 256, 0, s>>>(B.info, B.kept, B.points, B.max_kept, B.max_points, W);
+    GOFPID_CUDA_TRY(cudaGetLastError());
+    if (n_launches) *n_launches = 6;
     return GOFPID_OK;
 }
 

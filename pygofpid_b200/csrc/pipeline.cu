@@ -727,12 +727,16 @@ GOFPID_API int gofpid_pipeline_blobs(gofpid_pipeline *p, int stream_idx, gofpid_
     const gofpid_blob *kb = F->h_kept + (size_t)stream_idx * B.max_kept;
     const int32_t *pts = F->h_points + (size_t)stream_idx * B.max_points * 2;
     // the reference's order: descending raster order of each component's first pixel
-    std::vector<int> order(nk);
-    for (int i = 0; i < nk; i++) order[i] = i;
+    // (blobs enclosed by another blob were flagged on the device: RETR_EXTERNAL drops them)
+    std::vector<int> order;
+    order.reserve(nk);
+    for (int i = 0; i < nk; i++)
+        if (!kb[i].nested) order.push_back(i);
     std::sort(order.begin(), order.end(), [&](int a, int b) { return kb[a].first > kb[b].first; });
+    const int nout = (int)order.size();
     int total = 0;
-    for (int i = 0; i < nk; i++) total += kb[order[i]].n_points;
-    if (n_blobs) *n_blobs = nk;
+    for (int i = 0; i < nout; i++) total += kb[order[i]].n_points;
+    if (n_blobs) *n_blobs = nout;
     if (n_points) *n_points = total;
     if (fi.overflow) {
         set_error("blob capacity exceeded (flags %d): components %d/%d, kept %d/%d, points %d/%d",
@@ -740,12 +744,12 @@ GOFPID_API int gofpid_pipeline_blobs(gofpid_pipeline *p, int stream_idx, gofpid_
         return GOFPID_ERR_OVERFLOW;
     }
     if (!h_blobs && !h_points) return GOFPID_OK; // size query
-    if (nk > blob_capacity || total > point_capacity) {
-        set_error("output capacity too small: need %d blobs, %d points", nk, total);
+    if (nout > blob_capacity || total > point_capacity) {
+        set_error("output capacity too small: need %d blobs, %d points", nout, total);
         return GOFPID_ERR_INVALID;
     }
     int off = 0;
-    for (int i = 0; i < nk; i++) {
+    for (int i = 0; i < nout; i++) {
         gofpid_blob b = kb[order[i]];
         if (h_points) memcpy(h_points + (size_t)off * 2, pts + (size_t)b.point_offset * 2, sizeof(int32_t) * 2 * b.n_points);
         b.point_offset = off;
