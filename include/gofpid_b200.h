@@ -229,6 +229,12 @@ GOFPID_API int gofpid_blur_u8(const uint8_t *d_src, size_t src_pitch, uint8_t *d
 GOFPID_API int gofpid_morph_u8(const uint8_t *d_src, size_t src_pitch, uint8_t *d_dst,
                                size_t dst_pitch, int H, int W, const gofpid_morph_op *ops,
                                int n_ops, void *stream);
+/* Same chain on the bit-plane kernel the pipeline uses: the mask may only hold 0 and the given
+ * `levels` (1..3 ascending values, e.g. {127, 255}); other values are an input contract
+ * violation (they are read as the largest level not above them). */
+GOFPID_API int gofpid_morph_levels_u8(const uint8_t *d_src, size_t src_pitch, uint8_t *d_dst,
+                                      size_t dst_pitch, int H, int W, const gofpid_morph_op *ops,
+                                      int n_ops, const int *levels, int n_levels, void *stream);
 /* 8-connected labelling of a u8 mask (non-zero = foreground) into canonical int32 labels. */
 GOFPID_API int gofpid_ccl_u8(const uint8_t *d_mask, size_t mask_pitch, int32_t *d_labels,
                              size_t labels_pitch, int H, int W, void *stream);

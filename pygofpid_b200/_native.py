@@ -102,6 +102,8 @@ SIGNATURES = {
                                   ct.c_int, ct.c_double, _vp]),
     "gofpid_morph_u8": (ct.c_int, [_vp, _sz, _vp, _sz, ct.c_int, ct.c_int, ct.POINTER(MorphOp), ct.c_int,
                                    _vp]),
+    "gofpid_morph_levels_u8": (ct.c_int, [_vp, _sz, _vp, _sz, ct.c_int, ct.c_int, ct.POINTER(MorphOp), ct.c_int,
+                                          ct.POINTER(ct.c_int), ct.c_int, _vp]),
     "gofpid_ccl_u8": (ct.c_int, [_vp, _sz, _vp, _sz, ct.c_int, ct.c_int, _vp]),
 }
 

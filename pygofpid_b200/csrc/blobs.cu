@@ -24,6 +24,8 @@
 // pitch of the label image); pipeline.cu converts to the canonical dense numbering.
 #include "common.cuh"
 
+#include <stdlib.h>
+
 namespace gofpid {
 
 constexpr int CCL_TW = 64;  // one 64-bit word of class bits per tile row
@@ -85,6 +87,281 @@ __device__ __forceinline__ void uf_union_g(int32_t *lab, int a, int b)
     }
 }
 
+
+// ------------------------------------------------------------------------------------
+// 0. run-based labelling on the foreground bit image (the usual path)
+// ------------------------------------------------------------------------------------
+// After morphology a foreground mask is a few compact blobs: a 1080p frame has some thousand
+// horizontal runs.  One CTA per camera stream labels the whole frame in shared memory, with block
+// barriers instead of kernel boundaries between the phases:
+//   A  every warp owns a contiguous slice of the bit image, counts run starts and run ends
+//      (bit tricks on 32-pixel words) -> exclusive bases per warp;
+//   B  second sweep: the k-th start and the k-th end of the frame belong to the same run, so runs
+//      (y, xs, xe) land in raster order, with the index of every row's first run;
+//   C  union-find over runs: a run is joined with the runs of the row above that overlap
+//      [xs-1, xe+1] (8-connectivity), found by binary search in that row's slice;
+//   D  roots get component slots in raster order of their first pixel (block scan);
+//   E  area / bounding box per component with shared-memory atomics;
+//   F  component records, and the label image filled along the runs only (the tracer asks which
+//      component a border pixel belongs to).
+// A frame with more runs or components than fit in shared memory raises the per-stream fallback
+// flag (info.reserved[1]) and is labelled by the tiled union-find kernels below instead.
+constexpr int RC_THREADS = 1024;
+constexpr int RC_MAX_COMP = 1024;                 // component slots in shared memory
+constexpr size_t RC_SMEM_BUDGET = 224 * 1024;     // bytes of dynamic shared memory
+
+struct RunCclPlan {
+    int max_runs;      // run capacity (0: the frame shape does not fit, always fall back)
+    size_t smem_bytes;
+};
+static RunCclPlan run_ccl_plan(int H)
+{
+    RunCclPlan P;
+    const size_t fixed = ((size_t)(H + 1) * 4 + 15) / 16 * 16 + (size_t)RC_MAX_COMP * 6 * 4;
+    P.max_runs = 0; P.smem_bytes = 0;
+    if (fixed + 4096 * 10 > RC_SMEM_BUDGET) return P;
+    P.max_runs = (int)((RC_SMEM_BUDGET - fixed) / 10) & ~7;
+    if (P.max_runs > 65535) P.max_runs = 65535;
+    P.smem_bytes = fixed + (size_t)P.max_runs * 10;
+    return P;
+}
+
+__device__ __forceinline__ int rc_find(const int *parent, int k)
+{
+    while (true) {
+        const int n = parent[k];
+        if (n == k) return k;
+        k = n;
+    }
+}
+__device__ __forceinline__ void rc_union(int *parent, int a, int b)
+{
+    while (true) {
+        a = rc_find(parent, a); b = rc_find(parent, b);
+        if (a == b) return;
+        if (a < b) { const int t = a; a = b; b = t; }
+        const int old = atomicMin(&parent[a], b);
+        if (old == a) return;
+        a = old;
+    }
+}
+
+__global__ void __launch_bounds__(RC_THREADS, 1)
+runs_ccl_kernel(const uint32_t *bitimg, int bit_pitch, size_t bit_stream, int32_t *labels, size_t LP,
+                size_t labels_stream, int32_t *comp, gofpid_frame_info *info, int max_blobs, int max_runs,
+                const FrameTick *tick, int H, int W)
+{
+    extern __shared__ __align__(16) unsigned char rsm[];
+    const int z = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int *rowstart = reinterpret_cast<int *>(rsm);                               // [H + 1]
+    int *cstat = rowstart + ((H + 1 + 3) & ~3);                                 // [6][RC_MAX_COMP]
+    int *parent = cstat + 6 * RC_MAX_COMP;                                      // [max_runs]
+    uint16_t *run_xs = reinterpret_cast<uint16_t *>(parent + max_runs);         // [max_runs]
+    uint16_t *run_xe = run_xs + max_runs;
+    uint16_t *run_y = run_xe + max_runs;
+    __shared__ int wtot[2][32];
+    __shared__ int sh_scan[32];
+    __shared__ int sh_total;
+
+    gofpid_frame_info *fi = info + z;
+    const uint32_t *img = bitimg + (size_t)z * bit_stream;
+    const int NWR = (W + 31) >> 5;
+    const int T = NWR * H;
+    const int chunk = (((T + 31) / 32) + 31) & ~31; // words per warp, a multiple of 32
+
+    // ---- A: count run starts / ends per warp slice ----------------------------------------
+    auto sweep = [&](auto &&body) {
+        int i = warp * chunk + lane;
+        int y = i / NWR, c = i - y * NWR;
+        for (int it = 0; it < chunk; it += 32) {
+            uint32_t starts = 0, ends = 0;
+            if (i < T) {
+                const uint32_t *r = img + (size_t)(y + 1) * bit_pitch + c; // r[0] = word c-1
+                const uint32_t prev = __ldg(r), cur = __ldg(r + 1), next = __ldg(r + 2);
+                starts = cur & ~((cur << 1) | (prev >> 31));
+                ends = cur & ~((cur >> 1) | (next << 31));
+            }
+            body(y, c, starts, ends, i < T);
+            i += 32; c += 32;
+            while (c >= NWR) { c -= NWR; y++; }
+        }
+    };
+    {
+        int ns = 0, ne = 0;
+        sweep([&](int, int, uint32_t starts, uint32_t ends, bool) { ns += __popc(starts); ne += __popc(ends); });
+        ns = __reduce_add_sync(0xffffffffu, ns);
+        ne = __reduce_add_sync(0xffffffffu, ne);
+        if (lane == 0) { wtot[0][warp] = ns; wtot[1][warp] = ne; }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        int a = wtot[0][lane], b = wtot[1][lane];
+        int ia = a, ib = b;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
+            if (lane >= o) { ia += ta; ib += tb; }
+        }
+        wtot[0][lane] = ia - a; wtot[1][lane] = ib - b; // exclusive bases
+        if (lane == 31) sh_total = ia;
+    }
+    __syncthreads();
+    const int N = sh_total;
+    const bool fallback = max_runs == 0 || N > max_runs;
+    if (tid == 0) {
+        fi->n_components = 0; fi->n_candidates = 0; fi->n_kept = 0; fi->n_points = 0;
+        fi->overflow = 0; fi->frame_index = tick ? tick->nframes : 0;
+        fi->reserved[0] = 0; fi->reserved[1] = fallback ? 1 : 0;
+    }
+    if (fallback) return;
+
+    // ---- B: runs in raster order ---------------------------------------------------------------
+    {
+        int bs = wtot[0][warp], be = wtot[1][warp];
+        sweep([&](int y, int c, uint32_t starts, uint32_t ends, bool valid) {
+            const int cnt = __popc(starts) | (__popc(ends) << 16);
+            int inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, inc, o);
+                if (lane >= o) inc += t;
+            }
+            const int tot = __shfl_sync(0xffffffffu, inc, 31);
+            const int ex = inc - cnt;
+            int ks = bs + (ex & 0xffff), ke = be + (ex >> 16);
+            if (valid && c == 0) rowstart[y] = ks;
+            for (uint32_t m = starts; m; m &= m - 1) {
+                run_xs[ks] = (uint16_t)(32 * c + __ffs(m) - 1);
+                run_y[ks] = (uint16_t)y;
+                parent[ks] = ks;
+                ks++;
+            }
+            for (uint32_t m = ends; m; m &= m - 1) run_xe[ke++] = (uint16_t)(32 * c + __ffs(m) - 1);
+            bs += tot & 0xffff; be += tot >> 16;
+        });
+        if (tid == 0) rowstart[H] = N;
+    }
+    __syncthreads();
+
+    // ---- C: unions with the row above -----------------------------------------------------------
+    for (int k = tid; k < N; k += RC_THREADS) {
+        const int y = run_y[k];
+        if (y == 0) continue;
+        const int a = (int)run_xs[k] - 1, b = (int)run_xe[k] + 1;
+        int lo = rowstart[y - 1], hi = rowstart[y];
+        const int end = hi;
+        while (lo < hi) { // first run of the row above with xe >= a
+            const int mid = (lo + hi) >> 1;
+            if ((int)run_xe[mid] < a) lo = mid + 1; else hi = mid;
+        }
+        for (int j = lo; j < end && (int)run_xs[j] <= b; j++) rc_union(parent, k, j);
+    }
+    __syncthreads();
+
+    // ---- D: flatten; roots get slots in raster order -----------------------------------------
+    for (int k = tid; k < N; k += RC_THREADS) parent[k] = rc_find(parent, k);
+    __syncthreads();
+    const int per = (N + RC_THREADS - 1) / RC_THREADS;
+    const int k0 = min(tid * per, N), k1 = min(k0 + per, N);
+    int mine = 0;
+    for (int k = k0; k < k1; k++) mine += parent[k] == k;
+    int incl = mine;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= o) incl += t;
+    }
+    if (lane == 31) sh_scan[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        int v = sh_scan[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += t;
+        }
+        sh_scan[lane] = v;
+    }
+    __syncthreads();
+    const int ncomp = sh_scan[31];
+    if (ncomp > RC_MAX_COMP && ncomp <= max_blobs) { // more components than slots here: tiled path
+        if (tid == 0) fi->reserved[1] = 1;
+        return;
+    }
+    const int nslot = min(ncomp, min(max_blobs, RC_MAX_COMP));
+    int *c_first = cstat, *c_x0 = cstat + RC_MAX_COMP, *c_y0 = cstat + 2 * RC_MAX_COMP,
+        *c_x1 = cstat + 3 * RC_MAX_COMP, *c_y1 = cstat + 4 * RC_MAX_COMP, *c_area = cstat + 5 * RC_MAX_COMP;
+    {
+        int slot = (warp ? sh_scan[warp - 1] : 0) + incl - mine;
+        // roots are marked -(slot + 1); non-root runs keep pointing at their (flattened) root
+        for (int k = k0; k < k1; k++)
+            if (parent[k] == k) {
+                if (slot < nslot) {
+                    c_first[slot] = (int)((size_t)run_y[k] * LP + run_xs[k]);
+                    c_x0[slot] = 0x7fffffff; c_y0[slot] = 0x7fffffff; c_x1[slot] = -1; c_y1[slot] = -1;
+                    c_area[slot] = 0;
+                }
+                parent[k] = -(slot + 1);
+                slot++;
+            }
+    }
+    __syncthreads();
+
+    // ---- E: component statistics ------------------------------------------------------------------
+    for (int k = tid; k < N; k += RC_THREADS) {
+        int p = parent[k];
+        if (p >= 0) p = parent[p];
+        const int slot = -p - 1;
+        if (slot >= nslot) continue; // beyond the handle's capacity (overflow is flagged below)
+        const int xs = run_xs[k], xe = run_xe[k], y = run_y[k];
+        atomicAdd(&c_area[slot], xe - xs + 1);
+        atomicMin(&c_x0[slot], xs); atomicMax(&c_x1[slot], xe);
+        atomicMin(&c_y0[slot], y); atomicMax(&c_y1[slot], y);
+    }
+    __syncthreads();
+
+    // ---- F: records + labels along the runs ----------------------------------------------------
+    if (tid == 0) {
+        fi->n_components = ncomp;
+        if (ncomp > max_blobs) fi->overflow = 1;
+    }
+    for (int s = tid; s < nslot; s += RC_THREADS) {
+        int32_t *cr = comp + ((size_t)z * max_blobs + s) * CR_SIZE;
+        cr[CR_FIRST] = c_first[s]; cr[CR_X0] = c_x0[s]; cr[CR_Y0] = c_y0[s]; cr[CR_X1] = c_x1[s];
+        cr[CR_Y1] = c_y1[s]; cr[CR_AREA] = c_area[s];
+    }
+    int32_t *lab = labels + (size_t)z * labels_stream;
+    for (int k = warp; k < N; k += RC_THREADS / 32) {
+        int p = parent[k];
+        if (p >= 0) p = parent[p];
+        const int slot = -p - 1;
+        if (slot >= nslot) continue;
+        const int v = c_first[slot] + 1;
+        int32_t *row = lab + (size_t)run_y[k] * LP;
+        for (int x = (int)run_xs[k] + lane; x <= (int)run_xe[k]; x += 32) row[x] = v;
+    }
+}
+
+// foreground bit image of a u8 mask (frames whose morphology step did not already produce it)
+__global__ void __launch_bounds__(256)
+pack_bits_kernel(ImageU8 mask, uint32_t *bitimg, int bit_pitch, size_t bit_stream, int H, int W)
+{
+    const int x = (blockIdx.x * 32 + threadIdx.x) * 4, y = blockIdx.y * 8 + threadIdx.y;
+    if (y >= H) return; // warp-uniform: a warp is one row of 128 pixels
+    const uint8_t *mrow = mask.base + (size_t)blockIdx.z * mask.stream_stride + (size_t)y * mask.pitch;
+    uint32_t mw = 0;
+    if (x < W) mw = *reinterpret_cast<const uint32_t *>(mrow + x);
+    unsigned nib = 0;
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+        if (x + j < W && ((mw >> (8 * j)) & 255) != 0) nib |= 1u << j;
+    const unsigned lane = threadIdx.x;
+    const unsigned word = __reduce_or_sync(0xffu << (lane & 24), nib << (4 * (lane & 7)));
+    if ((lane & 7) == 0 && x < W)
+        bitimg[(size_t)blockIdx.z * bit_stream + (size_t)(y + 1) * bit_pitch + 1 + (x >> 5)] = word;
+}
+
 // ------------------------------------------------------------------------------------
 // 1. tile-local labelling (run based)
 // ------------------------------------------------------------------------------------
@@ -110,8 +387,9 @@ __device__ __forceinline__ int run_end(unsigned long long S, int x)
 
 __global__ void __launch_bounds__(CCL_THREADS)
 label_tiles_kernel(ImageU8 mask, int32_t *labels, size_t LP, size_t labels_stream, int H, int W,
-                   gofpid_frame_info *info, const FrameTick *tick)
+                   gofpid_frame_info *info, int force)
 {
+    if (!force && !info[blockIdx.z].reserved[1]) return; // labelled by runs_ccl_kernel
     __shared__ int lab[CCL_TW * CCL_TH];
     __shared__ unsigned int Fw[CCL_TH][2]; // foreground bits of each tile row (two 32-bit halves)
     const int tx = threadIdx.x, ty = threadIdx.y; // blockDim = (16, CCL_TH)
@@ -119,12 +397,6 @@ label_tiles_kernel(ImageU8 mask, int32_t *labels, size_t LP, size_t labels_strea
     const int x0 = blockIdx.x * CCL_TW, y0 = blockIdx.y * CCL_TH;
     const int lx = tx * 4, x = x0 + lx, y = y0 + ty;
     const uint8_t *mrow = mask.base + (size_t)blockIdx.z * mask.stream_stride + (size_t)y * mask.pitch;
-
-    if (blockIdx.x == 0 && blockIdx.y == 0 && tx == 0 && ty == 0) {
-        gofpid_frame_info *fi = info + blockIdx.z;
-        fi->n_components = 0; fi->n_candidates = 0; fi->n_kept = 0; fi->n_points = 0;
-        fi->overflow = 0; fi->frame_index = tick ? tick->nframes : 0; fi->reserved[0] = 0; fi->reserved[1] = 0;
-    }
 
     uint32_t mw = 0;
     if (y < H && x < W) mw = *reinterpret_cast<const uint32_t *>(mrow + x); // padded pitch
@@ -210,8 +482,10 @@ label_tiles_kernel(ImageU8 mask, int32_t *labels, size_t LP, size_t labels_strea
 // 2. unions across tile borders
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(CCL_TW + 2 * CCL_TH)
-merge_tiles_kernel(ImageU8 mask, int32_t *labels, size_t LP, size_t labels_stream, int H, int W)
+merge_tiles_kernel(ImageU8 mask, int32_t *labels, size_t LP, size_t labels_stream, int H, int W,
+                   const gofpid_frame_info *info, int force)
 {
+    if (!force && !info[blockIdx.z].reserved[1]) return;
     const int t = threadIdx.x;
     const int x0 = blockIdx.x * CCL_TW, y0 = blockIdx.y * CCL_TH;
     int x, y;
@@ -246,6 +520,7 @@ flatten_kernel(ImageU8 mask, int32_t *labels, size_t LP, size_t labels_stream, i
                int32_t *comp, gofpid_frame_info *info, int max_blobs, uint32_t *bitimg,
                int bit_pitch, size_t bit_stream, int H, int W)
 {
+    if (!info[blockIdx.z].reserved[1]) return; // labelled by runs_ccl_kernel
     const int x = (blockIdx.x * 32 + threadIdx.x) * 4, y = blockIdx.y * 8 + threadIdx.y;
     if (y >= H) return; // warp-uniform: a warp is one row of 128 pixels
     int32_t *lab = labels + (size_t)blockIdx.z * labels_stream;
@@ -296,8 +571,9 @@ flatten_kernel(ImageU8 mask, int32_t *labels, size_t LP, size_t labels_stream, i
 // ------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 stats_kernel(ImageU8 mask, const int32_t *labels, size_t LP, size_t labels_stream,
-             const int32_t *slot, int32_t *comp, int max_blobs, int H, int W)
+             const int32_t *slot, int32_t *comp, const gofpid_frame_info *info, int max_blobs, int H, int W)
 {
+    if (!info[blockIdx.z].reserved[1]) return; // labelled by runs_ccl_kernel
     const int x = (blockIdx.x * 32 + threadIdx.x) * 4, y = blockIdx.y * 8 + threadIdx.y;
     const bool inside = y < H && x < W;
     const int32_t *lab = labels + (size_t)blockIdx.z * labels_stream;
@@ -791,34 +1067,55 @@ __global__ void __launch_bounds__(256)
 nest_kernel(gofpid_frame_info *info, gofpid_blob *kept, const int32_t *points, int max_kept, int max_points,
             int W)
 {
+    constexpr int CAP = 2048; // boxes staged in shared memory (further blobs are read from global)
+    __shared__ short4 box[CAP];
     const int z = blockIdx.x;
     gofpid_frame_info *fi = info + z;
     const int nk = min(fi->n_kept, max_kept);
+    if (nk < 2) return;
     gofpid_blob *kb = kept + (size_t)z * max_kept;
     const int32_t *pts = points + (size_t)z * max_points * 2;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+    for (int i = threadIdx.x; i < min(nk, CAP); i += blockDim.x)
+        box[i] = make_short4((short)kb[i].x0, (short)kb[i].y0, (short)kb[i].x1, (short)kb[i].y1);
+    __syncthreads();
+    auto get_box = [&](int i) -> short4 {
+        if (i < CAP) return box[i];
+        return make_short4((short)kb[i].x0, (short)kb[i].y0, (short)kb[i].x1, (short)kb[i].y1);
+    };
     for (int k = warp; k < nk; k += nwarps) {
-        const gofpid_blob bk = kb[k];
-        const int fy = bk.first / W, fx = bk.first - fy * W;
+        const short4 bk = get_box(k);
         bool nested = false;
-        for (int j = 0; j < nk && !nested; j++) {
-            if (j == k) continue;
-            const gofpid_blob bj = kb[j];
-            if (!(bj.x0 < bk.x0 && bj.y0 < bk.y0 && bj.x1 > bk.x1 && bj.y1 > bk.y1)) continue;
-            if (bj.n_points <= 0) continue;
-            const int32_t *cj = pts + (size_t)bj.point_offset * 2;
-            unsigned crossings = 0;
-            for (int i = lane; i < bj.n_points; i += 32) {
-                const int i2 = i + 1 == bj.n_points ? 0 : i + 1;
-                const int xa = cj[2 * i], ya = cj[2 * i + 1], xb = cj[2 * i2], yb = cj[2 * i2 + 1];
-                if ((ya > fy) != (yb > fy)) {
-                    const int xe = ya == fy ? xa : xb; // the endpoint on the ray's row
-                    if (fx < xe) crossings++;
-                }
+        int fy = 0, fx = 0;
+        bool have_first = false;
+        for (int j0 = 0; j0 < nk && !nested; j0 += 32) {
+            const int j = j0 + lane;
+            bool hit = false;
+            if (j < nk && j != k) {
+                const short4 bj = get_box(j);
+                hit = bj.x < bk.x && bj.y < bk.y && bj.z > bk.z && bj.w > bk.w;
             }
-#pragma unroll
-            for (int o = 16; o > 0; o >>= 1) crossings += __shfl_xor_sync(0xffffffffu, crossings, o);
-            nested = crossings & 1u;
+            unsigned m = __ballot_sync(0xffffffffu, hit);
+            while (m && !nested) {
+                const int jj = j0 + __ffs(m) - 1;
+                m &= m - 1;
+                if (!have_first) { const int f = kb[k].first; fy = f / W; fx = f - fy * W; have_first = true; }
+                const int np = kb[jj].n_points;
+                if (np <= 0) continue;
+                const int32_t *cj = pts + (size_t)kb[jj].point_offset * 2;
+                unsigned crossings = 0;
+                for (int i = lane; i < np; i += 32) {
+                    const int i2 = i + 1 == np ? 0 : i + 1;
+                    const int2 pa = *reinterpret_cast<const int2 *>(cj + 2 * i);
+                    const int2 pb = *reinterpret_cast<const int2 *>(cj + 2 * i2);
+                    if ((pa.y > fy) != (pb.y > fy)) {
+                        const int xe = pa.y == fy ? pa.x : pb.x; // the endpoint on the ray's row
+                        if (fx < xe) crossings++;
+                    }
+                }
+                crossings = __reduce_add_sync(0xffffffffu, crossings);
+                nested = crossings & 1u;
+            }
         }
         if (lane == 0 && nested) {
             kb[k].nested = 1;
@@ -830,31 +1127,55 @@ nest_kernel(gofpid_frame_info *info, gofpid_blob *kept, const int32_t *points, i
 // ------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------
-static int launch_labelling(ImageU8 mask, int32_t *labels, size_t LP, size_t labels_stream, int H,
-                            int W, int n_streams, gofpid_frame_info *info, const FrameTick *tick,
-                            cudaStream_t s)
+static int run_ccl_cap_override()
 {
-    const dim3 tgrid((W + CCL_TW - 1) / CCL_TW, (H + CCL_TH - 1) / CCL_TH, n_streams);
-    label_tiles_kernel<<<tgrid, dim3(16, CCL_TH), 0, s>>>(mask, labels, LP, labels_stream, H, W,
-                                                          info, tick);
+    const char *e = getenv("GOFPID_RUNS_CAP"); // tests: force the tiled fallback with a tiny capacity
+    return e ? atoi(e) : -1;
+}
+
+// labelling: runs in shared memory, tiled union-find for the streams that raised the fallback flag
+static int launch_labelling(ImageU8 mask, const uint32_t *bitimg, int bit_pitch, size_t bit_stream,
+                            int32_t *labels, size_t LP, size_t labels_stream, int32_t *comp, int max_blobs,
+                            int H, int W, int n_streams, gofpid_frame_info *info, const FrameTick *tick,
+                            int force_tiled, cudaStream_t s)
+{
+    RunCclPlan P = run_ccl_plan(H);
+    const int cap = run_ccl_cap_override();
+    if (cap >= 0 && cap < P.max_runs) P.max_runs = cap & ~7;
+    if (force_tiled) P.max_runs = 0;
+    if (P.max_runs == 0) P.smem_bytes = 0; // the kernel only raises the fallback flag
+    GOFPID_CUDA_TRY(cudaFuncSetAttribute(runs_ccl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)RC_SMEM_BUDGET));
+    runs_ccl_kernel<<<n_streams, RC_THREADS, P.smem_bytes, s>>>(bitimg, bit_pitch, bit_stream, labels, LP,
+                                                                labels_stream, comp, info, max_blobs,
+                                                                P.max_runs, tick, H, W);
     GOFPID_CUDA_TRY(cudaGetLastError());
-    merge_tiles_kernel<<<tgrid, CCL_TW + 2 * CCL_TH, 0, s>>>(mask, labels, LP, labels_stream, H, W);
+    const dim3 tgrid((W + CCL_TW - 1) / CCL_TW, (H + CCL_TH - 1) / CCL_TH, n_streams);
+    label_tiles_kernel<<<tgrid, dim3(16, CCL_TH), 0, s>>>(mask, labels, LP, labels_stream, H, W, info, 0);
+    GOFPID_CUDA_TRY(cudaGetLastError());
+    merge_tiles_kernel<<<tgrid, CCL_TW + 2 * CCL_TH, 0, s>>>(mask, labels, LP, labels_stream, H, W, info, 0);
     GOFPID_CUDA_TRY(cudaGetLastError());
     return GOFPID_OK;
 }
 
 int launch_blobs(const BlobBuffers &B, ImageU8 mask, int H, int W, int n_streams,
-                 const FrameTick *tick, cudaStream_t s, int *n_launches)
+                 const FrameTick *tick, cudaStream_t s, int *n_launches, bool bits_ready)
 {
-    GOFPID_TRY(launch_labelling(mask, B.labels, B.labels_pitch, B.labels_stream, H, W, n_streams,
-                                B.info, tick, s));
+    int n = 0;
     const dim3 pgrid((W + 127) / 128, (H + 7) / 8, n_streams);
+    if (!bits_ready) {
+        pack_bits_kernel<<<pgrid, dim3(32, 8), 0, s>>>(mask, B.bitimg, B.bit_pitch, B.bit_stream, H, W);
+        GOFPID_CUDA_TRY(cudaGetLastError());
+        n++;
+    }
+    GOFPID_TRY(launch_labelling(mask, B.bitimg, B.bit_pitch, B.bit_stream, B.labels, B.labels_pitch,
+                                B.labels_stream, B.comp, B.max_blobs, H, W, n_streams, B.info, tick, 0, s));
     flatten_kernel<<<pgrid, dim3(32, 8), 0, s>>>(mask, B.labels, B.labels_pitch, B.labels_stream,
                                                  B.slot, B.comp, B.info, B.max_blobs, B.bitimg,
                                                  B.bit_pitch, B.bit_stream, H, W);
     GOFPID_CUDA_TRY(cudaGetLastError());
     stats_kernel<<<pgrid, dim3(32, 8), 0, s>>>(mask, B.labels, B.labels_pitch, B.labels_stream,
-                                               B.slot, B.comp, B.max_blobs, H, W);
+                                               B.slot, B.comp, B.info, B.max_blobs, H, W);
     GOFPID_CUDA_TRY(cudaGetLastError());
     GOFPID_CUDA_TRY(cudaFuncSetAttribute(trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)TRACE_SMEM_BYTES));
@@ -865,7 +1186,7 @@ int launch_blobs(const BlobBuffers &B, ImageU8 mask, int H, int W, int n_streams
     GOFPID_CUDA_TRY(cudaGetLastError());
     nest_kernel<<<n_streams, 256, 0, s>>>(B.info, B.kept, B.points, B.max_kept, B.max_points, W);
     GOFPID_CUDA_TRY(cudaGetLastError());
-    if (n_launches) *n_launches = 6;
+    if (n_launches) *n_launches = n + 7;
     return GOFPID_OK;
 }
 
@@ -897,27 +1218,41 @@ int launch_canonical_labels(const uint8_t *mask, size_t mask_pitch, const int32_
 int launch_ccl_only(const uint8_t *d_mask, size_t mask_pitch, int32_t *d_labels,
                     size_t labels_pitch_elems, int H, int W, cudaStream_t s)
 {
-    // stage a padded copy of the mask (the tile kernel reads whole words) and provisional labels
+    // stage a padded copy of the mask (the kernels read whole words), its bit image, provisional
+    // labels and component records; same labelling sequence as the pipeline.
+    // GOFPID_CCL_FORCE_TILED=1 sends everything through the tiled fallback kernels.
     const size_t MP = round_up((size_t)W, 128), LP = round_up((size_t)W, 4);
+    const int bit_pitch = (int)round_up((size_t)(W + 31) / 32 + 2, 4);
+    const size_t bit_words = (size_t)bit_pitch * (H + 2);
+    const int max_blobs = 1 << 16;
+    const char *e = getenv("GOFPID_CCL_FORCE_TILED");
+    const int force = e && e[0] == '1';
     uint8_t *pm = nullptr;
-    int32_t *pl = nullptr;
+    int32_t *pl = nullptr, *comp = nullptr, *slot = nullptr;
+    uint32_t *bits = nullptr;
     gofpid_frame_info *fi = nullptr;
     GOFPID_CUDA_TRY(cudaMalloc(&pm, MP * H));
     GOFPID_CUDA_TRY(cudaMalloc(&pl, LP * H * sizeof(int32_t)));
+    GOFPID_CUDA_TRY(cudaMalloc(&slot, LP * H * sizeof(int32_t)));
+    GOFPID_CUDA_TRY(cudaMalloc(&bits, bit_words * sizeof(uint32_t)));
+    GOFPID_CUDA_TRY(cudaMalloc(&comp, (size_t)max_blobs * CR_SIZE * sizeof(int32_t)));
     GOFPID_CUDA_TRY(cudaMalloc(&fi, sizeof(gofpid_frame_info)));
     int rc = GOFPID_OK;
     do {
-        if (cudaMemcpy2DAsync(pm, MP, d_mask, mask_pitch, W, H, cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
+        if (cudaMemsetAsync(bits, 0, bit_words * sizeof(uint32_t), s) != cudaSuccess ||
+            cudaMemsetAsync(pm, 0, MP * H, s) != cudaSuccess ||
+            cudaMemcpy2DAsync(pm, MP, d_mask, mask_pitch, W, H, cudaMemcpyDeviceToDevice, s) != cudaSuccess) {
             set_error("mask staging copy failed"); rc = GOFPID_ERR_CUDA; break;
         }
         ImageU8 m{pm, MP, 0};
-        rc = launch_labelling(m, pl, LP, 0, H, W, 1, fi, nullptr, s);
+        pack_bits_kernel<<<dim3((W + 127) / 128, (H + 7) / 8, 1), dim3(32, 8), 0, s>>>(m, bits, bit_pitch, 0, H, W);
+        rc = launch_labelling(m, bits, bit_pitch, 0, pl, LP, 0, comp, max_blobs, H, W, 1, fi, nullptr, force, s);
         if (rc) break;
         rc = launch_canonical_labels(pm, MP, pl, LP, d_labels, labels_pitch_elems, H, W, s);
         if (rc) break;
         if (cudaStreamSynchronize(s) != cudaSuccess) { set_error("labelling failed: %s", cudaGetErrorString(cudaGetLastError())); rc = GOFPID_ERR_CUDA; }
     } while (0);
-    cudaFree(pm); cudaFree(pl); cudaFree(fi);
+    cudaFree(pm); cudaFree(pl); cudaFree(slot); cudaFree(bits); cudaFree(comp); cudaFree(fi);
     return rc;
 }
 

@@ -170,13 +170,24 @@ struct MorphPlan {
     int halo_l, halo_r, halo_t, halo_b; // accumulated over the chain
     MorphRun *d_runs;                   // device copy of the run table
     int n_runs;
+    int anchored;                       // every SE contains its anchor (uniform tiles stay uniform)
     int tile_w, tile_h;                 // output tile per CTA
     size_t smem_bytes;
+    // bit-plane path (morph_bits_kernel): the mask only takes the values {0} + levels[0..n_levels)
+    // (ascending), so the chain runs on n_levels one-bit threshold planes, 32 pixels per word
+    int n_levels;                       // 0: byte path
+    int levels[3];
+    int bit_tile_h, bit_hw_l, bit_hw_r; // tile rows, halo words left / right (tile width = 256 px)
+    size_t bit_smem_bytes;
 };
+// Declares the set of non-zero values the chain's input can hold (at most 3); selects the bit-plane
+// kernel.  Called by the pipeline, which knows its detector's output alphabet.
+void morph_plan_set_levels(MorphPlan *plan, const int *levels, int n_levels);
 int morph_plan_create(const gofpid_morph_op *ops, int n_ops, MorphPlan *plan);
 void morph_plan_destroy(MorphPlan *plan);
+// bitimg (optional, bit-plane path only): also writes the foreground bit image the blob stage reads
 int launch_morph(const MorphPlan &plan, ImageU8 src, ImageU8 dst, int H, int W, int n_streams,
-                 cudaStream_t s);
+                 cudaStream_t s, uint32_t *bitimg = nullptr, int bit_pitch = 0, size_t bit_stream = 0);
 
 // blobs ------------------------------------------------------------------------
 struct BlobBuffers {
@@ -195,8 +206,9 @@ struct BlobBuffers {
     int max_blobs, max_kept, max_points;
     double area_min;
 };
+// bits_ready: the morphology kernel already wrote B.bitimg for this mask
 int launch_blobs(const BlobBuffers &B, ImageU8 mask, int H, int W, int n_streams,
-                 const FrameTick *tick, cudaStream_t s, int *n_launches);
+                 const FrameTick *tick, cudaStream_t s, int *n_launches, bool bits_ready);
 int launch_canonical_labels(const uint8_t *mask, size_t mask_pitch, const int32_t *labels, size_t LP,
                             int32_t *out, size_t out_pitch_elems, int H, int W, cudaStream_t s);
 int launch_ccl_only(const uint8_t *d_mask, size_t mask_pitch, int32_t *d_labels,

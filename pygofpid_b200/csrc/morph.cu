@@ -35,6 +35,7 @@ int morph_plan_create(const gofpid_morph_op *ops, int n_ops, MorphPlan *plan)
         return GOFPID_ERR_UNSUPPORTED;
     }
     std::vector<MorphRun> runs;
+    int anchored = 1; // every structuring element contains its anchor
     for (int i = 0; i < n_ops; i++) {
         const gofpid_morph_op &o = ops[i];
         if (o.op != GOFPID_MORPH_ERODE && o.op != GOFPID_MORPH_DILATE) {
@@ -59,6 +60,7 @@ int morph_plan_create(const gofpid_morph_op *ops, int n_ops, MorphPlan *plan)
             return GOFPID_ERR_UNSUPPORTED;
         }
         d.is_rect = nz == o.kh * o.kw;
+        if (!o.kernel[d.ay * o.kw + d.ax]) anchored = 0;
         d.run_begin = (int)runs.size();
         if (!d.is_rect) {
             for (int r = 0; r < o.kh; r++) {
@@ -80,6 +82,7 @@ int morph_plan_create(const gofpid_morph_op *ops, int n_ops, MorphPlan *plan)
         plan->halo_l += d.ax; plan->halo_r += o.kw - 1 - d.ax;
     }
     plan->n_ops = n_ops;
+    plan->anchored = anchored;
     plan->n_runs = (int)runs.size();
     if (!runs.empty()) {
         GOFPID_CUDA_TRY(cudaMalloc(&plan->d_runs, runs.size() * sizeof(MorphRun)));
@@ -321,9 +324,10 @@ morph_chain_kernel(MorphPlan plan, ImageU8 src, ImageU8 dst, int H, int W)
 
     const int tw4 = plan.tile_w >> 2;
     const int cbase = (MORPH_SLACK + hl4) >> 2; // buffer word column of x0
-    if (plan.n_ops > 0 && uniform != 3) {
-        // every in-image pixel the tile can see is 0 (or every one is 255): min / max over any
-        // structuring element reproduces that value, so the whole chain is the identity here
+    if (plan.n_ops > 0 && uniform != 3 && plan.anchored) {
+        // every in-image pixel the tile can see is 0 (or every one is 255): min / max over a
+        // structuring element that contains its anchor reproduces that value, so the whole chain
+        // is the identity here
         const uint32_t v = (uniform & 1) ? 0xffffffffu : 0u;
         for (int i = tid; i < plan.tile_h * tw4; i += MORPH_THREADS) {
             const int r = i / tw4, wc = i - r * tw4;
@@ -375,9 +379,270 @@ morph_chain_kernel(MorphPlan plan, ImageU8 src, ImageU8 dst, int H, int W)
     }
 }
 
-int launch_morph(const MorphPlan &plan, ImageU8 src, ImageU8 dst, int H, int W, int n_streams,
-                 cudaStream_t s)
+
+// =====================================================================================
+// bit-plane path
+// =====================================================================================
+// Inside the pipeline the mask that reaches the chain only holds the detector's alphabet: 0 and
+// at most three non-zero levels (MOG2 / KNN: shadow value and 255; frame differencing: 255, or
+// 84 / 85 for colour frames).  Flat erosion / dilation commute with thresholding, so the chain
+// is evaluated on one-bit threshold planes  P_i = (mask >= level_i)  with 32 pixels per word:
+// a horizontal run of the structuring element is a handful of funnel shifts and ANDs (window
+// doubling on a 64-bit register), the vertical pass of a rectangle is one AND per row, and the
+// grey-level result is rebuilt from the planes on the way out.  A CTA owns 256 x tile_h pixels,
+// stages tile + accumulated halo (whole halo WORDS left and right) as bits, and also emits the
+// foreground bit image the blob stage works on.
+constexpr int MB_THREADS = 256;
+constexpr int MB_TWW = 8; // tile width in 32-pixel words
+
+void morph_plan_set_levels(MorphPlan *plan, const int *levels, int n_levels)
 {
+    plan->n_levels = 0;
+    if (plan->n_ops <= 0 || n_levels < 1 || n_levels > 3) return;
+    for (int i = 0; i < n_levels; i++) {
+        if (levels[i] < 1 || levels[i] > 255 || (i > 0 && levels[i] <= levels[i - 1])) return;
+        plan->levels[i] = levels[i];
+    }
+    // all taps outside the image (possible only without the anchor): OpenCV yields 255 / 0, which
+    // the planes reproduce only when the top level is 255
+    if (!plan->anchored && levels[n_levels - 1] != 255) return;
+    plan->bit_hw_l = (plan->halo_l + 31) / 32;
+    plan->bit_hw_r = (plan->halo_r + 31) / 32;
+    const int hmax = plan->halo_t > plan->halo_b ? plan->halo_t : plan->halo_b;
+    plan->bit_tile_h = hmax > 8 ? 64 : 32;
+    const size_t nw = plan->bit_hw_l + MB_TWW + plan->bit_hw_r;
+    const size_t rows = plan->bit_tile_h + plan->halo_t + plan->halo_b;
+    plan->bit_smem_bytes = 3 * (size_t)n_levels * rows * nw * sizeof(uint32_t);
+    if (plan->bit_smem_bytes > 160 * 1024) return; // enormous halo: stay on the byte path
+    plan->n_levels = n_levels;
+}
+
+// 4 bits -> 4 bytes of 0x00 / 0xff (bit i -> byte i)
+__device__ __forceinline__ uint32_t spread4(uint32_t n)
+{
+    return (((n & 15u) * 0x00204081u) & 0x01010101u) * 0xffu;
+}
+// 4 bytes -> 4 bits: byte i >= t  ->  bit i   (t4 = t replicated in the four bytes)
+__device__ __forceinline__ uint32_t ge4(uint32_t w, uint32_t t4)
+{
+    return ((__vcmpgeu4(w, t4) & 0x80808080u) * 0x00204081u) >> 28;
+}
+
+// AND (erode) / OR (dilate) of the taps dx0 .. dx0+len-1 of a bit row, for the 32 pixels of word b
+// (a, c: the words left and right of it).  -31 <= dx0, dx0 + len <= 32, len >= 1.
+template <bool DIL>
+__device__ __forceinline__ uint32_t run_window(uint32_t a, uint32_t b, uint32_t c, int dx0, int len)
+{
+    if (DIL) { a = ~a; b = ~b; c = ~c; } // OR = complement of AND of complements
+    uint32_t lo, hi;
+    if (dx0 < 0) { lo = __funnelshift_r(a, b, 32 + dx0); hi = __funnelshift_r(b, c, 32 + dx0); }
+    else { lo = __funnelshift_r(b, c, dx0); hi = c >> dx0; }
+    unsigned long long u = ((unsigned long long)hi << 32) | lo; // bit j = pixel 32w + dx0 + j
+    int cov = 1;
+    while (2 * cov <= len) { u &= u >> cov; cov *= 2; }
+    if (cov < len) u &= u >> (len - cov);
+    const uint32_t r = (uint32_t)u;
+    return DIL ? ~r : r;
+}
+
+struct BitGeom {
+    int NW, rows, plane; // words per row, rows, words per plane
+    int gx0, gy0, H, W;  // image coordinates of buffer bit (0, 0)
+};
+
+// bits of word column w that lie inside the image
+__device__ __forceinline__ uint32_t in_image_bits(const BitGeom &G, int w)
+{
+    const int gx = G.gx0 + 32 * w;
+    if (gx + 31 < 0 || gx >= G.W) return 0u;
+    uint32_t m = 0xffffffffu;
+    if (gx < 0) m &= 0xffffffffu << (-gx);
+    if (gx + 32 > G.W) m &= 0xffffffffu >> (gx + 32 - G.W);
+    return m;
+}
+
+template <bool DIL>
+__device__ __forceinline__ void run_op_bits(const MorphOpDev &op, const MorphRun *__restrict__ runs,
+                                            const uint32_t *A, uint32_t *T, uint32_t *B, int nl,
+                                            const BitGeom &G, int r0, int r1, uint32_t ident_next)
+{
+    const int tid = threadIdx.x;
+    const int NW = G.NW;
+    const uint32_t ident = DIL ? 0u : 0xffffffffu;
+    if (op.is_rect) {
+        // row pass over the rows the column pass reads
+        const int rr0 = r0 - op.ay, nr = (r1 - r0) + op.kh - 1;
+        const int per = nr * NW;
+        for (int i = tid; i < per * nl; i += MB_THREADS) {
+            const int l = i / per, q = i - l * per;
+            const int r = rr0 + q / NW, w = q % NW;
+            const uint32_t *row = A + (size_t)l * G.plane + (size_t)r * NW;
+            const uint32_t a = w > 0 ? row[w - 1] : ident, c = w + 1 < NW ? row[w + 1] : ident;
+            T[(size_t)l * G.plane + (size_t)r * NW + w] = run_window<DIL>(a, row[w], c, -op.ax, op.kw);
+        }
+        __syncthreads();
+    }
+    {
+        const int nr = r1 - r0;
+        const int per = nr * NW;
+        for (int i = tid; i < per * nl; i += MB_THREADS) {
+            const int l = i / per, q = i - l * per;
+            const int r = r0 + q / NW, w = q % NW;
+            uint32_t acc = ident;
+            if (op.is_rect) {
+                const uint32_t *t = T + (size_t)l * G.plane + (size_t)(r - op.ay) * NW + w;
+                for (int k = 0; k < op.kh; k++) acc = DIL ? (acc | t[(size_t)k * NW]) : (acc & t[(size_t)k * NW]);
+            } else {
+                for (int qi = op.run_begin; qi < op.run_end; qi++) {
+                    const MorphRun run = runs[qi];
+                    const uint32_t *row = A + (size_t)l * G.plane + (size_t)(r + run.dy) * NW;
+                    const uint32_t a = w > 0 ? row[w - 1] : ident, c = w + 1 < NW ? row[w + 1] : ident;
+                    const uint32_t v = run_window<DIL>(a, row[w], c, run.dx, run.len);
+                    acc = DIL ? (acc | v) : (acc & v);
+                }
+            }
+            // cells outside the image take the identity of the NEXT step (OpenCV ignores them)
+            const int gy = G.gy0 + r;
+            const uint32_t m = (gy >= 0 && gy < G.H) ? in_image_bits(G, w) : 0u;
+            B[(size_t)l * G.plane + (size_t)r * NW + w] = (acc & m) | (ident_next & ~m);
+        }
+    }
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(MB_THREADS)
+morph_bits_kernel(MorphPlan plan, ImageU8 src, ImageU8 dst, uint32_t *bitimg, int bit_pitch,
+                  size_t bit_stream, int H, int W)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    const int tid = threadIdx.x;
+    const int nl = plan.n_levels;
+    BitGeom G;
+    G.NW = plan.bit_hw_l + MB_TWW + plan.bit_hw_r;
+    G.rows = plan.bit_tile_h + plan.halo_t + plan.halo_b;
+    G.plane = G.rows * G.NW;
+    const int x0 = blockIdx.x * (MB_TWW * 32), y0 = blockIdx.y * plan.bit_tile_h;
+    G.gx0 = x0 - 32 * plan.bit_hw_l; G.gy0 = y0 - plan.halo_t; G.H = H; G.W = W;
+    uint32_t *A = reinterpret_cast<uint32_t *>(smem);
+    uint32_t *T = A + (size_t)nl * G.plane;
+    uint32_t *B = T + (size_t)nl * G.plane;
+    const uint8_t *sbase = src.base + (size_t)blockIdx.z * src.stream_stride;
+    uint8_t *dbase = dst.base + (size_t)blockIdx.z * dst.stream_stride;
+    const bool aligned = ((reinterpret_cast<uintptr_t>(sbase) | src.pitch) & 15) == 0;
+    const bool daligned = ((reinterpret_cast<uintptr_t>(dbase) | dst.pitch) & 15) == 0;
+    const uint32_t ident0 = plan.ops[0].op == GOFPID_MORPH_ERODE ? 0xffffffffu : 0u;
+    uint32_t lv4[3];
+#pragma unroll
+    for (int l = 0; l < 3; l++) lv4[l] = (uint32_t)(plan.levels[l] & 255) * 0x01010101u;
+
+    // ---- stage tile + halo as threshold bits; out-of-image cells get the first step's identity
+    bool any = false;
+    for (int i = tid; i < G.plane; i += MB_THREADS) {
+        const int r = i / G.NW, w = i - r * G.NW;
+        const int gy = G.gy0 + r, gx = G.gx0 + 32 * w;
+        uint32_t bits[3] = {0u, 0u, 0u};
+        const uint32_t m = (gy >= 0 && gy < H) ? in_image_bits(G, w) : 0u;
+        if (m) {
+            const uint8_t *row = sbase + (size_t)gy * src.pitch;
+#pragma unroll
+            for (int h = 0; h < 2; h++) {
+                uint32_t v[4] = {0u, 0u, 0u, 0u};
+                const int hx = gx + 16 * h;
+                if (aligned && hx >= 0 && (size_t)hx + 16 <= src.pitch) {
+                    const uint4 q = *reinterpret_cast<const uint4 *>(row + hx);
+                    v[0] = q.x; v[1] = q.y; v[2] = q.z; v[3] = q.w;
+                } else {
+                    for (int b = 0; b < 16; b++)
+                        if (hx + b >= 0 && hx + b < W) v[b >> 2] |= (uint32_t)row[hx + b] << (8 * (b & 3));
+                }
+#pragma unroll
+                for (int l = 0; l < 3; l++)
+                    if (l < nl)
+                        bits[l] |= (ge4(v[0], lv4[l]) | (ge4(v[1], lv4[l]) << 4) | (ge4(v[2], lv4[l]) << 8) |
+                                    (ge4(v[3], lv4[l]) << 12)) << (16 * h);
+            }
+        }
+#pragma unroll
+        for (int l = 0; l < 3; l++)
+            if (l < nl) A[(size_t)l * G.plane + i] = (bits[l] & m) | (ident0 & ~m);
+        any |= (bits[0] & m) != 0u;
+    }
+    const bool nonempty = __syncthreads_or(any) || !plan.anchored;
+
+    const int tile_h = plan.bit_tile_h;
+    if (nonempty) {
+        int r0 = 0, r1 = G.rows;
+        for (int k = 0; k < plan.n_ops; k++) {
+            const MorphOpDev &op = plan.ops[k];
+            r0 += op.ay; r1 -= op.kh - 1 - op.ay;
+            const uint32_t ident_next =
+                (k + 1 < plan.n_ops && plan.ops[k + 1].op == GOFPID_MORPH_ERODE) ? 0xffffffffu : 0u;
+            if (op.op == GOFPID_MORPH_DILATE) run_op_bits<true>(op, plan.d_runs, A, T, B, nl, G, r0, r1, ident_next);
+            else run_op_bits<false>(op, plan.d_runs, A, T, B, nl, G, r0, r1, ident_next);
+            uint32_t *t = A; A = B; B = t;
+        }
+    }
+    // (an empty tile -- no foreground anywhere the chain can see -- stays empty through a chain of
+    // structuring elements that contain their anchors)
+
+    // ---- grey levels back from the planes: 16 pixels (one uint4) per thread and step -----------
+    for (int i = tid; i < tile_h * MB_TWW * 2; i += MB_THREADS) {
+        const int r = i / (MB_TWW * 2), hw = i - r * (MB_TWW * 2);
+        const int w = hw >> 1, h = hw & 1;
+        const int gy = y0 + r, gx = x0 + 32 * w + 16 * h;
+        if (gy >= H || gx >= W) continue;
+        const size_t si = (size_t)(r + plan.halo_t) * G.NW + plan.bit_hw_l + w;
+        uint32_t p[3] = {0u, 0u, 0u};
+        if (nonempty) {
+#pragma unroll
+            for (int l = 0; l < 3; l++)
+                if (l < nl) p[l] = (A[(size_t)l * G.plane + si] >> (16 * h)) & 0xffffu;
+        }
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            uint32_t v = spread4(p[0] >> (4 * q)) & lv4[0];
+#pragma unroll
+            for (int l = 1; l < 3; l++)
+                if (l < nl) {
+                    const uint32_t ml = spread4(p[l] >> (4 * q));
+                    v = (v & ~ml) | (ml & lv4[l]);
+                }
+            o[q] = v;
+        }
+        uint8_t *row = dbase + (size_t)gy * dst.pitch;
+        if (daligned && (size_t)gx + 16 <= dst.pitch) {
+            *reinterpret_cast<uint4 *>(row + gx) = make_uint4(o[0], o[1], o[2], o[3]);
+        } else {
+            for (int b = 0; b < 16; b++)
+                if (gx + b < W) row[gx + b] = (uint8_t)(o[b >> 2] >> (8 * (b & 3)));
+        }
+        if (bitimg && h == 0) {
+            const uint32_t fg = nonempty ? A[si] : 0u; // plane 0 = (mask != 0)
+            bitimg[(size_t)blockIdx.z * bit_stream + (size_t)(gy + 1) * bit_pitch + 1 + (gx >> 5)] = fg;
+        }
+    }
+}
+
+int launch_morph(const MorphPlan &plan, ImageU8 src, ImageU8 dst, int H, int W, int n_streams,
+                 cudaStream_t s, uint32_t *bitimg, int bit_pitch, size_t bit_stream)
+{
+    if (plan.n_levels > 0) {
+        if (plan.bit_smem_bytes > 48 * 1024)
+            GOFPID_CUDA_TRY(cudaFuncSetAttribute(morph_bits_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)plan.bit_smem_bytes));
+        const dim3 grid((W + MB_TWW * 32 - 1) / (MB_TWW * 32), (H + plan.bit_tile_h - 1) / plan.bit_tile_h,
+                        n_streams);
+        morph_bits_kernel<<<grid, MB_THREADS, plan.bit_smem_bytes, s>>>(plan, src, dst, bitimg, bit_pitch,
+                                                                        bit_stream, H, W);
+        GOFPID_CUDA_TRY(cudaGetLastError());
+        return GOFPID_OK;
+    }
+    if (bitimg) {
+        set_error("internal: the byte morphology path does not produce the foreground bit image");
+        return GOFPID_ERR_INVALID;
+    }
+
     if (plan.smem_bytes > 200 * 1024) {
         set_error("morphology chain needs %zu bytes of shared memory (halo too large)",
                   plan.smem_bytes);

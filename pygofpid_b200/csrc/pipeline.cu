@@ -290,6 +290,20 @@ int build(gofpid_pipeline *p)
     }
 
     GOFPID_TRY(morph_plan_create(p->cfg.morph, p->cfg.n_morph, &p->morph));
+    {
+        // the detector's output alphabet selects the bit-plane morphology kernel
+        int lv[3], n = 0;
+        if (cfg.detector == GOFPID_DETECT_FD) {
+            if (C == 3) { lv[n++] = 84; lv[n++] = 85; } // uint8-wrapping channel mean (segmentation.py:64)
+            else lv[n++] = 255;
+        } else {
+            const int sv = cfg.shadow_value & 255;
+            if (cfg.detect_shadows && sv > 0 && sv < 255) lv[n++] = sv;
+            lv[n++] = 255;
+        }
+        const char *e = getenv("GOFPID_MORPH_BYTES");
+        if (!(e && e[0] == '1')) morph_plan_set_levels(&p->morph, lv, n);
+    }
 
     if (cfg.find_blobs) {
         if (cfg.max_blobs < 1 || cfg.max_kept < 1 || cfg.max_points < 1) {
@@ -349,8 +363,10 @@ int enqueue_stage_a(gofpid_pipeline *p, FrameSlot &F, const FrameSrc &src, cudaS
     launches += detect_launches_per_step(p->cfg.detector);
     if (prof) GOFPID_CUDA_TRY(cudaEventRecord(p->ev[1], s));
     if (p->cfg.n_morph > 0) {
+        const bool bits = p->morph.n_levels > 0 && p->cfg.find_blobs;
         GOFPID_TRY(launch_morph(p->morph, L.mask, ImageU8{F.d_final, p->mask_pitch, p->mask_stream},
-                                p->H, p->W, p->n_streams, s));
+                                p->H, p->W, p->n_streams, s, bits ? F.blobs.bitimg : nullptr,
+                                F.blobs.bit_pitch, F.blobs.bit_stream));
         launches += 1;
     }
     if (prof) GOFPID_CUDA_TRY(cudaEventRecord(p->ev[2], s));
@@ -364,7 +380,7 @@ int enqueue_stage_b(gofpid_pipeline *p, FrameSlot &F, cudaStream_t s, int *n_lau
     int nb = 0;
     if (p->cfg.find_blobs)
         GOFPID_TRY(launch_blobs(F.blobs, ImageU8{F.d_final, p->mask_pitch, p->mask_stream}, p->H, p->W,
-                                p->n_streams, nullptr, s, &nb));
+                                p->n_streams, nullptr, s, &nb, p->cfg.n_morph > 0 && p->morph.n_levels > 0));
     if (n_launches) *n_launches = nb;
     return GOFPID_OK;
 }
@@ -991,10 +1007,25 @@ GOFPID_API int gofpid_blur_u8(const uint8_t *d_src, size_t src_pitch, uint8_t *d
 GOFPID_API int gofpid_morph_u8(const uint8_t *d_src, size_t src_pitch, uint8_t *d_dst, size_t dst_pitch,
                                int H, int W, const gofpid_morph_op *ops, int n_ops, void *stream)
 {
+    return gofpid_morph_levels_u8(d_src, src_pitch, d_dst, dst_pitch, H, W, ops, n_ops, nullptr, 0, stream);
+}
+
+GOFPID_API int gofpid_morph_levels_u8(const uint8_t *d_src, size_t src_pitch, uint8_t *d_dst, size_t dst_pitch,
+                                      int H, int W, const gofpid_morph_op *ops, int n_ops,
+                                      const int *levels, int n_levels, void *stream)
+{
     if (!d_src || !d_dst || H <= 0 || W <= 0 || (n_ops > 0 && !ops)) { set_error("bad argument"); return GOFPID_ERR_INVALID; }
     if (gofpid_device_count() == 0) { set_error("no CUDA device available (no CPU fallback)"); return GOFPID_ERR_CUDA; }
     MorphPlan plan;
     GOFPID_TRY(morph_plan_create(ops, n_ops, &plan));
+    if (levels && n_levels > 0) {
+        morph_plan_set_levels(&plan, levels, n_levels);
+        if (n_ops > 0 && plan.n_levels == 0) {
+            morph_plan_destroy(&plan);
+            set_error("levels must be 1..3 ascending values in [1, 255]");
+            return GOFPID_ERR_INVALID;
+        }
+    }
     int rc = launch_morph(plan, ImageU8{const_cast<uint8_t *>(d_src), src_pitch, 0}, ImageU8{d_dst, dst_pitch, 0},
                           H, W, 1, (cudaStream_t)stream);
     if (rc == GOFPID_OK && cudaStreamSynchronize((cudaStream_t)stream) != cudaSuccess) {

@@ -299,8 +299,11 @@ def blur_u8(src, kind, ksize, sigma=0.0):
     return dst
 
 
-def morph_u8(src, ops):
-    """Fused chain of ('erode' | 'dilate', kernel) steps on a CUDA uint8 (H, W) tensor."""
+def morph_u8(src, ops, levels=None):
+    """Fused chain of ('erode' | 'dilate', kernel) steps on a CUDA uint8 (H, W) tensor.
+
+    `levels` (1..3 ascending values): the mask only holds 0 and these values; runs the bit-plane
+    kernel the pipeline uses instead of the byte kernel."""
     import torch
     H, W = src.shape
     dst = torch.empty_like(src)
@@ -312,6 +315,11 @@ def morph_u8(src, ops):
         arr[i].op = {"erode": nat.MORPH_ERODE, "dilate": nat.MORPH_DILATE}[op]
         arr[i].kh, arr[i].kw = k.shape
         arr[i].kernel = k.ctypes.data_as(ct.POINTER(ct.c_uint8))
+    if levels is not None:
+        lv = (ct.c_int * len(levels))(*[int(v) for v in levels])
+        nat.check(nat.lib().gofpid_morph_levels_u8(_dev_u8(src), W, _dev_u8(dst), W, H, W, arr, len(ops),
+                                                   lv, len(levels), torch.cuda.current_stream().cuda_stream))
+        return dst
     nat.check(nat.lib().gofpid_morph_u8(_dev_u8(src), W, _dev_u8(dst), W, H, W, arr, len(ops),
                                         torch.cuda.current_stream().cuda_stream))
     return dst

@@ -161,8 +161,12 @@ def _blob_masks():
     return out
 
 
-def test_blobs_match_reference_semantics():
-    """Feed masks through FD (|mask - 0| > 0 keeps them as they are) and compare the blob list."""
+@pytest.mark.parametrize("runs_cap", [None, 40])
+def test_blobs_match_reference_semantics(runs_cap, monkeypatch):
+    """Feed masks through FD (|mask - 0| > 0 keeps them as they are) and compare the blob list.
+    runs_cap=40 sends every frame with more than 40 runs through the tiled labelling fallback."""
+    if runs_cap is not None:
+        monkeypatch.setenv("GOFPID_RUNS_CAP", str(runs_cap))
     for M in _blob_masks():
         H, W = M.shape
         for area_min in (100.0, 0.5):

@@ -119,6 +119,50 @@ def test_morph_chains_bitexact(shape):
                                            int((got != want).sum()))
 
 
+BIT_SHAPES = MORPH_SHAPES + [(70, 600), (300, 257), (65, 1000)]
+
+
+@pytest.mark.parametrize("shape", BIT_SHAPES)
+def test_morph_bitplane_path_bitexact(shape):
+    """The pipeline's bit-plane kernel (threshold decomposition) against the oracle, for every
+    detector alphabet: {255}, {127, 255}, {84, 85}, three levels, W not a multiple of 16/32/256."""
+    torch = _torch()
+    from pygofpid_b200.hotpath import morph_u8
+    rs = np.random.RandomState(11)
+    r5 = np.ones((5, 5), np.uint8)
+    r3 = np.ones((3, 3), np.uint8)
+    lshape = np.array([[1, 0, 0], [1, 0, 0], [1, 1, 5]], np.uint8)
+    noanchor = np.array([[1, 0, 0, 0, 1]], np.uint8)  # anchor element is 0
+    chains = [
+        [("erode", r5), ("dilate", r5)],
+        [("erode", r5), ("dilate", r5), ("dilate", r5), ("erode", r5)],
+        [("erode", ellipse(15, 15)), ("dilate", ellipse(15, 15))],
+        [("dilate", r3), ("erode", ellipse(7, 5)), ("dilate", np.ones((2, 4), np.uint8))],
+        [("erode", lshape)], [("dilate", lshape)], [("erode", np.ones((4, 6), np.uint8))],
+        [("dilate", np.ones((7, 1), np.uint8)), ("erode", np.ones((1, 9), np.uint8))],
+        [("erode", noanchor)], [("dilate", noanchor), ("erode", noanchor)],
+        [("dilate", np.ones((31, 31), np.uint8))], [("erode", ellipse(31, 31)), ("dilate", ellipse(31, 31))],
+    ]
+    H, W = shape
+    for levels in ([255], [127, 255], [84, 85], [1, 128, 200]):
+        alphabet = np.array([0] + levels, np.uint8)
+        masks = [alphabet[rs.randint(0, len(alphabet), shape)],                      # dense noise
+                 alphabet[(rs.rand(H, W) < 0.03) * rs.randint(1, len(alphabet), shape)],  # sparse
+                 _grey_mask(rs, shape) if levels == [127, 255] else None,
+                 np.zeros(shape, np.uint8), np.full(shape, levels[-1], np.uint8)]
+        for M in masks:
+            if M is None:
+                continue
+            d = torch.from_numpy(np.ascontiguousarray(M)).cuda()
+            for chain in chains:
+                want = M
+                for name, se in chain:
+                    want = (cport.erode if name == "erode" else cport.dilate)(want, se)
+                got = morph_u8(d, chain, levels=levels).cpu().numpy()
+                assert np.array_equal(got, want), (shape, levels, [(n, s.shape) for n, s in chain],
+                                                   int((got != want).sum()))
+
+
 def _blob_mask(rs, H, W, density=None):
     import cv2
     if density is not None:
@@ -134,9 +178,16 @@ def _blob_mask(rs, H, W, density=None):
 
 @pytest.mark.parametrize("shape", [(20, 20), (16, 128), (17, 129), (40, 300), (97, 131), (240, 320),
                                    (1, 50), (50, 1), (200, 517)])
-def test_ccl_labels_bitexact(shape):
+@pytest.mark.parametrize("path", ["runs", "tiled", "runs_cap64"])
+def test_ccl_labels_bitexact(shape, path, monkeypatch):
+    """Both labelling paths: run-based in shared memory (the usual one) and the tiled union-find
+    fallback (forced, or reached because the frame has more runs than the capacity)."""
     torch = _torch()
     from pygofpid_b200.hotpath import ccl_u8
+    if path == "tiled":
+        monkeypatch.setenv("GOFPID_CCL_FORCE_TILED", "1")
+    elif path == "runs_cap64":
+        monkeypatch.setenv("GOFPID_RUNS_CAP", "64")
     rs = np.random.RandomState(11)
     H, W = shape
     masks = [_blob_mask(rs, H, W), _blob_mask(rs, H, W, 0.5), _blob_mask(rs, H, W, 0.62),
