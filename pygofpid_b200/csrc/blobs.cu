@@ -25,6 +25,7 @@
 #include "common.cuh"
 
 #include <stdlib.h>
+#include <string.h>
 
 namespace gofpid {
 
@@ -40,7 +41,7 @@ constexpr int TRACE_HT_SHIFT = 19;          // 32 - log2(TRACE_HT)
 constexpr size_t TRACE_SMEM_BYTES = (size_t)TRACE_MAX_CP * (8 + 24) + (size_t)TRACE_HT * 8;
 
 // component record layout (8 int32)
-enum { CR_FIRST = 0, CR_X0, CR_Y0, CR_X1, CR_Y1, CR_AREA, CR_PAD0, CR_PAD1, CR_SIZE };
+enum { CR_FIRST = 0, CR_X0, CR_Y0, CR_X1, CR_Y1, CR_AREA, CR_RSTART, CR_NRUNS, CR_SIZE }; // (run slice: runs path only)
 
 // ------------------------------------------------------------------------------------
 // union-find primitives (value v: 0 = OUTSIDE, else element index v-1)
@@ -92,52 +93,155 @@ __device__ __forceinline__ void uf_union_g(int32_t *lab, int a, int b)
 // 0. run-based labelling on the foreground bit image (the usual path)
 // ------------------------------------------------------------------------------------
 // After morphology a foreground mask is a few compact blobs: a 1080p frame has some thousand
-// horizontal runs.  One CTA per camera stream labels the whole frame in shared memory, with block
-// barriers instead of kernel boundaries between the phases:
-//   A  every warp owns a contiguous slice of the bit image, counts run starts and run ends
-//      (bit tricks on 32-pixel words) -> exclusive bases per warp;
-//   B  second sweep: the k-th start and the k-th end of the frame belong to the same run, so runs
-//      (y, xs, xe) land in raster order, with the index of every row's first run;
-//   C  union-find over runs: a run is joined with the runs of the row above that overlap
-//      [xs-1, xe+1] (8-connectivity), found by binary search in that row's slice;
-//   D  roots get component slots in raster order of their first pixel (block scan);
-//   E  area / bounding box per component with shared-memory atomics;
-//   F  component records, and the label image filled along the runs only (the tracer asks which
-//      component a border pixel belongs to).
-// A frame with more runs or components than fit in shared memory raises the per-stream fallback
-// flag (info.reserved[1]) and is labelled by the tiled union-find kernels below instead.
+// horizontal runs.  Two kernels:
+//   runs_extract_kernel  many CTAs, one band of RX_ROWS image rows each: run starts and run ends
+//       from bit tricks on the 32-pixel words (the k-th start and the k-th end of a band belong
+//       to the same run), a block scan, ONE atomicAdd per band to reserve a slice of the
+//       stream's run list, and the runs (y, xs, xe) written in raster order inside the band,
+//       with every row's slice [rowstart, rowend).
+//   runs_ccl_kernel      one CTA per camera stream, everything in shared memory with block
+//       barriers between the phases:
+//       C  union-find over runs: a run is joined with the runs of the row above that overlap
+//          [xs-1, xe+1] (8-connectivity), found by binary search in that row's slice;
+//       D  flatten; roots get component slots (block scan);
+//       E  area / bounding box / raster-first pixel per component with shared-memory atomics;
+//       F  component records, and the label image filled along the runs only (the tracer asks
+//          which component a border pixel belongs to).
+// A frame with more runs or components than fit raises the per-stream fallback flag
+// (info.reserved[1]) and is labelled by the tiled union-find kernels below instead.
+constexpr int RX_ROWS = 8;      // image rows per extraction CTA
+constexpr int RX_THREADS = 256;
+constexpr int RX_MAXW = 8;      // words per thread at most (bands up to 2048 words)
 constexpr int RC_THREADS = 1024;
 constexpr int RC_MAX_COMP = 1024;                 // component slots in shared memory
 constexpr size_t RC_SMEM_BUDGET = 224 * 1024;     // bytes of dynamic shared memory
 
-struct RunCclPlan {
-    int max_runs;      // run capacity (0: the frame shape does not fit, always fall back)
-    size_t smem_bytes;
-};
-static RunCclPlan run_ccl_plan(int H)
+// run capacity per stream for frames of H rows (0: the shape does not fit, always fall back)
+int run_ccl_capacity(int H, int bit_pitch)
 {
-    RunCclPlan P;
-    const size_t fixed = ((size_t)(H + 1) * 4 + 15) / 16 * 16 + (size_t)RC_MAX_COMP * 6 * 4;
-    P.max_runs = 0; P.smem_bytes = 0;
-    if (fixed + 4096 * 10 > RC_SMEM_BUDGET) return P;
-    P.max_runs = (int)((RC_SMEM_BUDGET - fixed) / 10) & ~7;
-    if (P.max_runs > 65535) P.max_runs = 65535;
-    P.smem_bytes = fixed + (size_t)P.max_runs * 10;
-    return P;
+    if (RX_ROWS * bit_pitch > RX_THREADS * RX_MAXW) return 0;
+    const size_t fixed = (size_t)2 * ((H + 3) & ~3) * 4 + (size_t)RC_MAX_COMP * 8 * 4;
+    if (fixed + 4096 * 10 > RC_SMEM_BUDGET) return 0;
+    int n = (int)((RC_SMEM_BUDGET - fixed) / 10) & ~7;
+    return n > 65528 ? 65528 : n;
+}
+static size_t run_ccl_smem(int H, int max_runs)
+{
+    return (size_t)2 * ((H + 3) & ~3) * 4 + (size_t)RC_MAX_COMP * 8 * 4 + (size_t)max_runs * 10;
 }
 
+__global__ void __launch_bounds__(RX_THREADS)
+runs_extract_kernel(const uint32_t *bitimg, int bit_pitch, size_t bit_stream, RunList R, int H)
+{
+    __shared__ int sh_scan[RX_THREADS / 32];
+    __shared__ int sh_base;
+    const int z = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int y0 = blockIdx.x * RX_ROWS;
+    const int rows = min(RX_ROWS, H - y0);
+    const int nw = rows * bit_pitch;                  // physical words of the band (guards included)
+    const int k = (nw + RX_THREADS - 1) / RX_THREADS; // consecutive words per thread (<= RX_MAXW)
+    const uint32_t *base = bitimg + (size_t)z * bit_stream + (size_t)(y0 + 1) * bit_pitch;
+    const int j0 = tid * k;
+    // guard words are zero, so a run never continues across a row end: no boundary tests
+    uint32_t wv[RX_MAXW + 2];
+#pragma unroll
+    for (int i = 0; i < RX_MAXW + 2; i++) {
+        const int j = j0 - 1 + i;
+        wv[i] = (i < k + 2 && j >= 0 && j < nw) ? __ldg(base + j) : 0u;
+    }
+    uint32_t st[RX_MAXW], en[RX_MAXW];
+    int cnt = 0;
+#pragma unroll
+    for (int i = 0; i < RX_MAXW; i++) {
+        const uint32_t cur = i < k ? wv[i + 1] : 0u; // (slot k + 1 holds the next thread's first word)
+        st[i] = cur & ~((cur << 1) | (wv[i] >> 31));
+        en[i] = cur & ~((cur >> 1) | (wv[i + 2] << 31));
+        cnt += __popc(st[i]) | (__popc(en[i]) << 16);
+    }
+    int inc = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, inc, o);
+        if (lane >= o) inc += t;
+    }
+    if (lane == 31) sh_scan[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int v = lane < RX_THREADS / 32 ? sh_scan[lane] : 0;
+#pragma unroll
+        for (int o = 1; o < RX_THREADS / 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, v, o);
+            if (lane >= o) v += t;
+        }
+        if (lane < RX_THREADS / 32) sh_scan[lane] = v;
+        if (lane == RX_THREADS / 32 - 1) sh_base = atomicAdd(R.count + z, v & 0xffff);
+    }
+    __syncthreads();
+    const int total = sh_scan[RX_THREADS / 32 - 1] & 0xffff;
+    const int gbase = sh_base;
+    const bool fits = gbase + total <= R.max_runs;
+    const int ex = (warp ? sh_scan[warp - 1] : 0) + inc - cnt;
+    int ks = gbase + (ex & 0xffff), ke = gbase + (ex >> 16);
+    uint16_t *xs = R.xs + (size_t)z * R.max_runs, *xe = R.xe + (size_t)z * R.max_runs,
+             *ry = R.y + (size_t)z * R.max_runs;
+    int *rowstart = R.rowstart + (size_t)z * R.row_pitch, *rowend = R.rowend + (size_t)z * R.row_pitch;
+    int y = j0 / bit_pitch, c = j0 - y * bit_pitch; // c: physical word column (logical + 1)
+#pragma unroll
+    for (int i = 0; i < RX_MAXW; i++) {
+        if (i < k && j0 + i < nw) {
+            if (c == 0) { // first word of a row (a guard word): the row's slice starts here
+                rowstart[y0 + y] = ks;
+                if (y > 0) rowend[y0 + y - 1] = ks;
+            }
+            if (fits) {
+                const int x0 = 32 * (c - 1);
+                for (uint32_t m = st[i]; m; m &= m - 1) {
+                    xs[ks] = (uint16_t)(x0 + __ffs(m) - 1);
+                    ry[ks] = (uint16_t)(y0 + y);
+                    ks++;
+                }
+                for (uint32_t m = en[i]; m; m &= m - 1) xe[ke++] = (uint16_t)(x0 + __ffs(m) - 1);
+            } else {
+                ks += __popc(st[i]);
+            }
+            if (++c == bit_pitch) { c = 0; y++; }
+        }
+    }
+    if (tid == 0) rowend[y0 + rows - 1] = gbase + total;
+}
+
+// Union-find over run indices in shared memory.  Edges always lead to a node that stopped being
+// a root later than the node they leave (unions link a root to a root; path halving replaces a
+// parent by that parent's parent), so the forest stays acyclic under any interleaving; the loops
+// are bounded all the same, so that a bug can only produce wrong labels, never a hung device.
+constexpr int RC_GUARD = 1 << 17;
 __device__ __forceinline__ int rc_find(const int *parent, int k)
 {
-    while (true) {
+    for (int it = 0; it < RC_GUARD; it++) {
         const int n = parent[k];
         if (n == k) return k;
         k = n;
     }
+    return k;
+}
+// find with path halving (plain stores: losing a race only loses a shortcut)
+__device__ __forceinline__ int rc_find_halve(int *parent, int k)
+{
+    for (int it = 0; it < RC_GUARD; it++) {
+        const int p = parent[k];
+        if (p == k) return k;
+        const int g = parent[p];
+        if (g == p) return p;
+        parent[k] = g;
+        k = g;
+    }
+    return k;
 }
 __device__ __forceinline__ void rc_union(int *parent, int a, int b)
 {
-    while (true) {
-        a = rc_find(parent, a); b = rc_find(parent, b);
+    for (int it = 0; it < RC_GUARD; it++) {
+        a = rc_find_halve(parent, a); b = rc_find_halve(parent, b);
         if (a == b) return;
         if (a < b) { const int t = a; a = b; b = t; }
         const int old = atomicMin(&parent[a], b);
@@ -146,120 +250,103 @@ __device__ __forceinline__ void rc_union(int *parent, int a, int b)
     }
 }
 
+#ifdef GOFPID_TRACE_DEBUG
+__device__ long long g_rc_dbg[16];
+#define RC_T(k) do { __syncthreads(); if (threadIdx.x == 0 && blockIdx.x == 0) g_rc_dbg[k] = clock64(); } while (0)
+#else
+#define RC_T(k)
+#endif
+
 __global__ void __launch_bounds__(RC_THREADS, 1)
-runs_ccl_kernel(const uint32_t *bitimg, int bit_pitch, size_t bit_stream, int32_t *labels, size_t LP,
-                size_t labels_stream, int32_t *comp, gofpid_frame_info *info, int max_blobs, int max_runs,
-                const FrameTick *tick, int H, int W)
+runs_ccl_kernel(RunList R, int32_t *labels, size_t LP, size_t labels_stream, int32_t *comp,
+                gofpid_frame_info *info, int max_blobs, int max_runs, const FrameTick *tick, int H, int W)
 {
     extern __shared__ __align__(16) unsigned char rsm[];
     const int z = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int *rowstart = reinterpret_cast<int *>(rsm);                               // [H + 1]
-    int *cstat = rowstart + ((H + 1 + 3) & ~3);                                 // [6][RC_MAX_COMP]
-    int *parent = cstat + 6 * RC_MAX_COMP;                                      // [max_runs]
+    const int HP = (H + 3) & ~3;
+    int *rowstart = reinterpret_cast<int *>(rsm);                               // [HP]
+    int *rowend = rowstart + HP;                                                // [HP]
+    int *cstat = rowend + HP;                                                   // [8][RC_MAX_COMP]
+    int *parent = cstat + 8 * RC_MAX_COMP;                                      // [max_runs]
     uint16_t *run_xs = reinterpret_cast<uint16_t *>(parent + max_runs);         // [max_runs]
     uint16_t *run_xe = run_xs + max_runs;
     uint16_t *run_y = run_xe + max_runs;
-    __shared__ int wtot[2][32];
     __shared__ int sh_scan[32];
-    __shared__ int sh_total;
 
     gofpid_frame_info *fi = info + z;
-    const uint32_t *img = bitimg + (size_t)z * bit_stream;
-    const int NWR = (W + 31) >> 5;
-    const int T = NWR * H;
-    const int chunk = (((T + 31) / 32) + 31) & ~31; // words per warp, a multiple of 32
-
-    // ---- A: count run starts / ends per warp slice ----------------------------------------
-    auto sweep = [&](auto &&body) {
-        int i = warp * chunk + lane;
-        int y = i / NWR, c = i - y * NWR;
-        for (int it = 0; it < chunk; it += 32) {
-            uint32_t starts = 0, ends = 0;
-            if (i < T) {
-                const uint32_t *r = img + (size_t)(y + 1) * bit_pitch + c; // r[0] = word c-1
-                const uint32_t prev = __ldg(r), cur = __ldg(r + 1), next = __ldg(r + 2);
-                starts = cur & ~((cur << 1) | (prev >> 31));
-                ends = cur & ~((cur >> 1) | (next << 31));
-            }
-            body(y, c, starts, ends, i < T);
-            i += 32; c += 32;
-            while (c >= NWR) { c -= NWR; y++; }
-        }
-    };
-    {
-        int ns = 0, ne = 0;
-        sweep([&](int, int, uint32_t starts, uint32_t ends, bool) { ns += __popc(starts); ne += __popc(ends); });
-        ns = __reduce_add_sync(0xffffffffu, ns);
-        ne = __reduce_add_sync(0xffffffffu, ne);
-        if (lane == 0) { wtot[0][warp] = ns; wtot[1][warp] = ne; }
-    }
-    __syncthreads();
-    if (warp == 0) {
-        int a = wtot[0][lane], b = wtot[1][lane];
-        int ia = a, ib = b;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const int ta = __shfl_up_sync(0xffffffffu, ia, o), tb = __shfl_up_sync(0xffffffffu, ib, o);
-            if (lane >= o) { ia += ta; ib += tb; }
-        }
-        wtot[0][lane] = ia - a; wtot[1][lane] = ib - b; // exclusive bases
-        if (lane == 31) sh_total = ia;
-    }
-    __syncthreads();
-    const int N = sh_total;
+    RC_T(0);
+    const int N = R.count[z];
     const bool fallback = max_runs == 0 || N > max_runs;
+    __syncthreads(); // every thread has read the count
     if (tid == 0) {
+        R.count[z] = 0; // for the slot's next frame
+        R.n_labelled[z] = fallback ? 0 : N;
         fi->n_components = 0; fi->n_candidates = 0; fi->n_kept = 0; fi->n_points = 0;
         fi->overflow = 0; fi->frame_index = tick ? tick->nframes : 0;
         fi->reserved[0] = 0; fi->reserved[1] = fallback ? 1 : 0;
     }
     if (fallback) return;
 
-    // ---- B: runs in raster order ---------------------------------------------------------------
+    // ---- runs and row slices into shared memory ---------------------------------------------------
     {
-        int bs = wtot[0][warp], be = wtot[1][warp];
-        sweep([&](int y, int c, uint32_t starts, uint32_t ends, bool valid) {
-            const int cnt = __popc(starts) | (__popc(ends) << 16);
-            int inc = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, inc, o);
-                if (lane >= o) inc += t;
-            }
-            const int tot = __shfl_sync(0xffffffffu, inc, 31);
-            const int ex = inc - cnt;
-            int ks = bs + (ex & 0xffff), ke = be + (ex >> 16);
-            if (valid && c == 0) rowstart[y] = ks;
-            for (uint32_t m = starts; m; m &= m - 1) {
-                run_xs[ks] = (uint16_t)(32 * c + __ffs(m) - 1);
-                run_y[ks] = (uint16_t)y;
-                parent[ks] = ks;
-                ks++;
-            }
-            for (uint32_t m = ends; m; m &= m - 1) run_xe[ke++] = (uint16_t)(32 * c + __ffs(m) - 1);
-            bs += tot & 0xffff; be += tot >> 16;
-        });
-        if (tid == 0) rowstart[H] = N;
+        const uint16_t *gxs = R.xs + (size_t)z * R.max_runs, *gxe = R.xe + (size_t)z * R.max_runs,
+                       *gy = R.y + (size_t)z * R.max_runs;
+        // (max_runs is a multiple of 8: the three lists are 16-byte aligned, copied 8 runs at a time)
+        for (int i = tid; i < (N + 7) / 8; i += RC_THREADS) {
+            reinterpret_cast<uint4 *>(run_xs)[i] = __ldg(reinterpret_cast<const uint4 *>(gxs) + i);
+            reinterpret_cast<uint4 *>(run_xe)[i] = __ldg(reinterpret_cast<const uint4 *>(gxe) + i);
+            reinterpret_cast<uint4 *>(run_y)[i] = __ldg(reinterpret_cast<const uint4 *>(gy) + i);
+        }
+        const int *grs = R.rowstart + (size_t)z * R.row_pitch, *gre = R.rowend + (size_t)z * R.row_pitch;
+        for (int y = tid; y < H; y += RC_THREADS) { rowstart[y] = __ldg(grs + y); rowend[y] = __ldg(gre + y); }
     }
     __syncthreads();
+    RC_T(3);
 
     // ---- C: unions with the row above -----------------------------------------------------------
-    for (int k = tid; k < N; k += RC_THREADS) {
+    // (1) every run points at the FIRST run of the row above that touches it: one plain store per
+    // run, a forest whose edges all go up one image row; (2) pointer jumping flattens the vertical
+    // chains in log(height) rounds; (3) the remaining overlaps -- where branches of a blob meet --
+    // are merged root to root with atomicMin.
+    auto overlap_range = [&](int k, int &lo, int &end, int &b) {
         const int y = run_y[k];
-        if (y == 0) continue;
-        const int a = (int)run_xs[k] - 1, b = (int)run_xe[k] + 1;
-        int lo = rowstart[y - 1], hi = rowstart[y];
-        const int end = hi;
+        lo = end = 0; b = 0;
+        if (y == 0) return;
+        const int a = (int)run_xs[k] - 1;
+        b = (int)run_xe[k] + 1;
+        lo = rowstart[y - 1];
+        int hi = rowend[y - 1];
+        end = hi;
         while (lo < hi) { // first run of the row above with xe >= a
             const int mid = (lo + hi) >> 1;
             if ((int)run_xe[mid] < a) lo = mid + 1; else hi = mid;
         }
-        for (int j = lo; j < end && (int)run_xs[j] <= b; j++) rc_union(parent, k, j);
+        if (lo < end && (int)run_xs[lo] > b) end = lo; // nothing touches
+    };
+    for (int k = tid; k < N; k += RC_THREADS) {
+        int lo, end, b;
+        overlap_range(k, lo, end, b);
+        parent[k] = lo < end ? lo : k;
     }
     __syncthreads();
+    for (int round = 0; round < 16; round++) {
+        bool changed = false;
+        for (int k = tid; k < N; k += RC_THREADS) {
+            const int p = parent[k], g = parent[p];
+            if (g != p) { parent[k] = g; changed = true; }
+        }
+        if (!__syncthreads_or(changed)) break;
+    }
+    for (int k = tid; k < N; k += RC_THREADS) {
+        int lo, end, b;
+        overlap_range(k, lo, end, b);
+        for (int j = lo + 1; j < end && (int)run_xs[j] <= b; j++) rc_union(parent, k, j);
+    }
+    __syncthreads();
+    RC_T(4);
 
-    // ---- D: flatten; roots get slots in raster order -----------------------------------------
+    // ---- D: flatten; roots get slots ------------------------------------------------------------
     for (int k = tid; k < N; k += RC_THREADS) parent[k] = rc_find(parent, k);
     __syncthreads();
     const int per = (N + RC_THREADS - 1) / RC_THREADS;
@@ -291,56 +378,101 @@ runs_ccl_kernel(const uint32_t *bitimg, int bit_pitch, size_t bit_stream, int32_
     }
     const int nslot = min(ncomp, min(max_blobs, RC_MAX_COMP));
     int *c_first = cstat, *c_x0 = cstat + RC_MAX_COMP, *c_y0 = cstat + 2 * RC_MAX_COMP,
-        *c_x1 = cstat + 3 * RC_MAX_COMP, *c_y1 = cstat + 4 * RC_MAX_COMP, *c_area = cstat + 5 * RC_MAX_COMP;
+        *c_x1 = cstat + 3 * RC_MAX_COMP, *c_y1 = cstat + 4 * RC_MAX_COMP, *c_area = cstat + 5 * RC_MAX_COMP,
+        *c_nruns = cstat + 6 * RC_MAX_COMP, *c_rstart = cstat + 7 * RC_MAX_COMP;
     {
         int slot = (warp ? sh_scan[warp - 1] : 0) + incl - mine;
         // roots are marked -(slot + 1); non-root runs keep pointing at their (flattened) root
         for (int k = k0; k < k1; k++)
             if (parent[k] == k) {
                 if (slot < nslot) {
-                    c_first[slot] = (int)((size_t)run_y[k] * LP + run_xs[k]);
+                    c_first[slot] = 0x7fffffff;
                     c_x0[slot] = 0x7fffffff; c_y0[slot] = 0x7fffffff; c_x1[slot] = -1; c_y1[slot] = -1;
-                    c_area[slot] = 0;
+                    c_area[slot] = 0; c_nruns[slot] = 0;
                 }
                 parent[k] = -(slot + 1);
                 slot++;
             }
     }
     __syncthreads();
+    RC_T(5);
 
-    // ---- E: component statistics ------------------------------------------------------------------
+    // ---- E: component statistics; every run learns its slot -------------------------------------
+    // (bands land in the run list in any order, so the smallest index is not the raster-first run:
+    // the first pixel is the minimum of y * LP + xs over the component)
     for (int k = tid; k < N; k += RC_THREADS) {
         int p = parent[k];
         if (p >= 0) p = parent[p];
         const int slot = -p - 1;
         if (slot >= nslot) continue; // beyond the handle's capacity (overflow is flagged below)
         const int xs = run_xs[k], xe = run_xe[k], y = run_y[k];
+        atomicMin(&c_first[slot], (int)((size_t)y * LP + xs));
         atomicAdd(&c_area[slot], xe - xs + 1);
+        atomicAdd(&c_nruns[slot], 1);
         atomicMin(&c_x0[slot], xs); atomicMax(&c_x1[slot], xe);
         atomicMin(&c_y0[slot], y); atomicMax(&c_y1[slot], y);
     }
     __syncthreads();
+    RC_T(6);
 
-    // ---- F: records + labels along the runs ----------------------------------------------------
-    if (tid == 0) {
-        fi->n_components = ncomp;
-        if (ncomp > max_blobs) fi->overflow = 1;
+    // ---- F: the runs grouped by component (what the tracer walks), records, per-run labels ----------
+    {
+        // exclusive scan of the run counts over the slots (RC_MAX_COMP == RC_THREADS: one slot per thread)
+        static_assert(RC_MAX_COMP == RC_THREADS, "one slot per thread");
+        const int mineF = tid < nslot ? c_nruns[tid] : 0;
+        int inc = mineF;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int t = __shfl_up_sync(0xffffffffu, inc, o);
+            if (lane >= o) inc += t;
+        }
+        __syncthreads(); // sh_scan is free again
+        if (lane == 31) sh_scan[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            int v = sh_scan[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int t = __shfl_up_sync(0xffffffffu, v, o);
+                if (lane >= o) v += t;
+            }
+            sh_scan[lane] = v;
+        }
+        __syncthreads();
+        const int rstart = (warp ? sh_scan[warp - 1] : 0) + inc - mineF;
+        if (tid < nslot) {
+            c_rstart[tid] = rstart;
+            int32_t *cr = comp + ((size_t)z * max_blobs + tid) * CR_SIZE;
+            cr[CR_FIRST] = c_first[tid]; cr[CR_X0] = c_x0[tid]; cr[CR_Y0] = c_y0[tid]; cr[CR_X1] = c_x1[tid];
+            cr[CR_Y1] = c_y1[tid]; cr[CR_AREA] = c_area[tid]; cr[CR_RSTART] = rstart; cr[CR_NRUNS] = mineF;
+            c_nruns[tid] = 0; // becomes the scatter cursor
+        }
+        if (tid == 0) {
+            fi->n_components = ncomp;
+            if (ncomp > max_blobs) fi->overflow = 1;
+        }
     }
-    for (int s = tid; s < nslot; s += RC_THREADS) {
-        int32_t *cr = comp + ((size_t)z * max_blobs + s) * CR_SIZE;
-        cr[CR_FIRST] = c_first[s]; cr[CR_X0] = c_x0[s]; cr[CR_Y0] = c_y0[s]; cr[CR_X1] = c_x1[s];
-        cr[CR_Y1] = c_y1[s]; cr[CR_AREA] = c_area[s];
+    __syncthreads();
+    {
+        uint2 *byc = R.byc + (size_t)z * R.max_runs;
+        int32_t *rlabel = R.label + (size_t)z * R.max_runs;
+        for (int k = tid; k < N; k += RC_THREADS) {
+            int p = parent[k];
+            if (p >= 0) p = parent[p];
+            const int slot = -p - 1;
+            int v = 0;
+            if (slot < nslot) {
+                v = c_first[slot] + 1;
+                const int pos = c_rstart[slot] + atomicAdd(&c_nruns[slot], 1);
+                byc[pos] = make_uint2(((uint32_t)run_y[k] << 16) | run_xs[k], run_xe[k]);
+            }
+            rlabel[k] = v;
+        }
     }
-    int32_t *lab = labels + (size_t)z * labels_stream;
-    for (int k = warp; k < N; k += RC_THREADS / 32) {
-        int p = parent[k];
-        if (p >= 0) p = parent[p];
-        const int slot = -p - 1;
-        if (slot >= nslot) continue;
-        const int v = c_first[slot] + 1;
-        int32_t *row = lab + (size_t)run_y[k] * LP;
-        for (int x = (int)run_xs[k] + lane; x <= (int)run_xe[k]; x += 32) row[x] = v;
-    }
+    RC_T(7);
+#ifdef GOFPID_TRACE_DEBUG
+    if (threadIdx.x == 0 && blockIdx.x == 0) { g_rc_dbg[8] = N; g_rc_dbg[9] = ncomp; }
+#endif
 }
 
 // foreground bit image of a u8 mask (frames whose morphology step did not already produce it)
@@ -360,6 +492,21 @@ pack_bits_kernel(ImageU8 mask, uint32_t *bitimg, int bit_pitch, size_t bit_strea
     const unsigned word = __reduce_or_sync(0xffu << (lane & 24), nib << (4 * (lane & 7)));
     if ((lane & 7) == 0 && x < W)
         bitimg[(size_t)blockIdx.z * bit_stream + (size_t)(y + 1) * bit_pitch + 1 + (x >> 5)] = word;
+}
+
+// label image from the run list (not on the hot path: gofpid_pipeline_labels / gofpid_ccl_u8 only).
+// One warp per run; streams labelled by the tiled fallback already have their label image.
+__global__ void __launch_bounds__(256)
+fill_labels_kernel(RunList R, int z, const gofpid_frame_info *info, int32_t *labels, size_t LP)
+{
+    if (info->reserved[1]) return;
+    const int k = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (k >= R.n_labelled[z]) return;
+    const int v = R.label[(size_t)z * R.max_runs + k];
+    if (v <= 0) return; // component beyond the handle's capacity
+    const int y = R.y[(size_t)z * R.max_runs + k], xs = R.xs[(size_t)z * R.max_runs + k],
+              xe = R.xe[(size_t)z * R.max_runs + k];
+    for (int x = xs + lane; x <= xe; x += 32) labels[(size_t)y * LP + x] = v;
 }
 
 // ------------------------------------------------------------------------------------
@@ -731,7 +878,7 @@ __device__ int trace_segment(const BitView &V, int x, int y, int b, int xs, int 
 }
 
 __global__ void __launch_bounds__(TRACE_THREADS)
-trace_kernel(const int32_t *labels, size_t LP, size_t labels_stream, const int32_t *comp,
+trace_kernel(const int32_t *labels, size_t LP, size_t labels_stream, RunList R, const int32_t *comp,
              gofpid_frame_info *info, gofpid_blob *kept, int32_t *points, int max_blobs,
              int max_kept, int max_points, double area_min, const uint32_t *bitimg, int bit_pitch,
              size_t bit_stream, int H, int W)
@@ -753,6 +900,9 @@ trace_kernel(const int32_t *labels, size_t LP, size_t labels_stream, const int32
     const int32_t *lab = labels + (size_t)z * labels_stream;
     gofpid_frame_info *fi = info + z;
     const int ncomp = min(fi->n_components, max_blobs);
+    // labelled by runs: a component's border pixels come from its own runs; tiled fallback: from
+    // the bit image inside its box, filtered with the label image
+    const bool by_runs = fi->reserved[1] == 0;
     const int tid = threadIdx.x;
     BitView bv; bv.img = bitimg + (size_t)z * bit_stream; bv.pitch = bit_pitch;
 
@@ -833,10 +983,9 @@ trace_kernel(const int32_t *labels, size_t LP, size_t labels_stream, const int32
             total = sh_warp[31];
             return ((tid >> 5) ? sh_warp[(tid >> 5) - 1] : 0) + incl - mine;
         };
-        // hash-selected border pixels of one bit-image word of the box
-        auto word_cands = [&](int i, int &y, int &xw) -> uint32_t {
-            const int ry = i / wpr, wc = w0 + (i - ry * wpr);
-            y = by0 + ry; xw = (wc << 5) - 32;
+        // hash-selected border pixels of bit-image word wc of image row y, columns [xlo, xhi]
+        auto cands_at = [&](int y, int wc, int xlo, int xhi) -> uint32_t {
+            const int xw = (wc << 5) - 32;
             const uint32_t *r = bv.img + (size_t)y * bv.pitch + wc; // row y - 1
             uint32_t all = 0xffffffffu;
 #pragma unroll
@@ -845,10 +994,10 @@ trace_kernel(const int32_t *labels, size_t LP, size_t labels_stream, const int32
                                g = __ldg(r + q * bv.pitch + 1);
                 all &= c & ((c << 1) | (l >> 31)) & ((c >> 1) | (g << 31));
             }
-            // foreground with a background 8-neighbour, inside the box columns
+            // foreground with a background 8-neighbour, inside the columns asked for
             uint32_t cand = __ldg(r + bv.pitch) & ~all;
-            if (bx0 > xw) cand &= ~0u << min(bx0 - xw, 31);
-            if (bx1 < xw + 31) cand &= ~0u >> (xw + 31 - bx1);
+            if (xlo > xw) cand &= ~0u << min(xlo - xw, 31);
+            if (xhi < xw + 31) cand &= ~0u >> (xw + 31 - xhi);
             if (rmask) {
                 uint32_t keep = 0;
                 for (uint32_t m = cand; m; m &= m - 1) {
@@ -859,12 +1008,29 @@ trace_kernel(const int32_t *labels, size_t LP, size_t labels_stream, const int32
             }
             return cand;
         };
-        // visit states of a candidate pixel: direction b foreground, b+1 background.  Pixels of
-        // other components inside the box are dropped: their borders may leave the box, where
-        // nothing is a checkpoint, and following them would take arbitrarily long.
+        // the thread's share of the words that can hold border pixels of the component
+        const uint2 *cruns = R.byc + (size_t)z * R.max_runs + cr[CR_RSTART];
+        const int nruns = by_runs ? cr[CR_NRUNS] : 0;
+        auto for_each_word = [&](auto &&f) {
+            if (by_runs) {
+                for (int i = tid; i < nruns; i += TRACE_THREADS) {
+                    const uint2 rr = __ldg(cruns + i);
+                    const int y = (int)(rr.x >> 16), xs_ = (int)(rr.x & 0xffffu), xe_ = (int)rr.y;
+                    for (int wc = (xs_ + 32) >> 5; wc <= (xe_ + 32) >> 5; wc++) f(y, wc, xs_, xe_);
+                }
+            } else {
+                for (int i = tid; i < wpr * bh; i += TRACE_THREADS) {
+                    const int ry = i / wpr;
+                    f(by0 + ry, w0 + (i - ry * wpr), bx0, bx1);
+                }
+            }
+        };
+        // visit states of a candidate pixel: direction b foreground, b+1 background.  In the box
+        // scan, pixels of other components inside the box are dropped: their borders may leave the
+        // box, where nothing is a checkpoint, and following them would take arbitrarily long.
         const int root = first + 1;
         auto visit_states = [&](int x, int y) -> unsigned {
-            if (lab[(size_t)y * LP + x] != root) return 0u;
+            if (!by_runs && lab[(size_t)y * LP + x] != root) return 0u;
             const unsigned nb = bv.nb(x, y);
             unsigned starts = nb & ~((nb >> 1) | (nb << 7)) & 0xffu;
             if (x == xs && y == ys) starts &= ~(1u << b0); // that one is checkpoint 0
@@ -874,20 +1040,16 @@ trace_kernel(const int32_t *labels, size_t LP, size_t labels_stream, const int32
             for (int i = tid; i < TRACE_HT; i += TRACE_THREADS) ht_keys[i] = 0;
             // ---- A: candidate pixels ------------------------------------------------------
             int mine = 0;
-            for (int i = tid; i < wpr * bh; i += TRACE_THREADS) {
-                int y, xw;
-                mine += __popc(word_cands(i, y, xw));
-            }
+            for_each_word([&](int y, int wc, int xlo, int xhi) { mine += __popc(cands_at(y, wc, xlo, xhi)); });
             int ncand;
             int slot = block_scan(mine, ncand);
             bool retry = ncand > CAND_CAP;
             int nstates = 0;
             if (!retry) {
-                for (int i = tid; i < wpr * bh; i += TRACE_THREADS) {
-                    int y, xw;
-                    for (uint32_t m = word_cands(i, y, xw); m; m &= m - 1)
-                        cand_list[slot++] = (y << 16) | (xw + __ffs(m) - 1);
-                }
+                for_each_word([&](int y, int wc, int xlo, int xhi) {
+                    for (uint32_t m = cands_at(y, wc, xlo, xhi); m; m &= m - 1)
+                        cand_list[slot++] = (y << 16) | ((wc << 5) - 32 + __ffs(m) - 1);
+                });
                 __syncthreads();
                 // ---- B: states per candidate ----------------------------------------------
                 mine = 0;
@@ -1042,6 +1204,11 @@ trace_kernel(const int32_t *labels, size_t LP, size_t labels_stream, const int32
 }
 
 #ifdef GOFPID_TRACE_DEBUG
+extern "C" __attribute__((visibility("default"))) void gofpid_debug_rc_dump(long long *out)
+{
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_rc_dbg, sizeof(long long) * 16);
+}
 extern "C" __attribute__((visibility("default"))) int gofpid_debug_trace_dump(long long *out)
 {
     int n = 0;
@@ -1127,28 +1294,52 @@ nest_kernel(gofpid_frame_info *info, gofpid_blob *kept, const int32_t *points, i
 // ------------------------------------------------------------------------------------
 // launchers
 // ------------------------------------------------------------------------------------
-static int run_ccl_cap_override()
+int run_list_alloc(RunList *R, int H, int bit_pitch, int n_streams)
 {
-    const char *e = getenv("GOFPID_RUNS_CAP"); // tests: force the tiled fallback with a tiny capacity
-    return e ? atoi(e) : -1;
+    memset(R, 0, sizeof(*R));
+    R->max_runs = run_ccl_capacity(H, bit_pitch);
+    R->row_pitch = (H + 3) & ~3;
+    const size_t n = (size_t)(R->max_runs ? R->max_runs : 8) * n_streams;
+    GOFPID_CUDA_TRY(cudaMalloc(&R->xs, n * sizeof(uint16_t)));
+    GOFPID_CUDA_TRY(cudaMalloc(&R->xe, n * sizeof(uint16_t)));
+    GOFPID_CUDA_TRY(cudaMalloc(&R->y, n * sizeof(uint16_t)));
+    GOFPID_CUDA_TRY(cudaMalloc(&R->rowstart, (size_t)R->row_pitch * n_streams * sizeof(int)));
+    GOFPID_CUDA_TRY(cudaMalloc(&R->rowend, (size_t)R->row_pitch * n_streams * sizeof(int)));
+    GOFPID_CUDA_TRY(cudaMalloc(&R->label, n * sizeof(int32_t)));
+    GOFPID_CUDA_TRY(cudaMalloc(&R->byc, n * sizeof(uint2)));
+    GOFPID_CUDA_TRY(cudaMalloc(&R->count, (size_t)n_streams * sizeof(int)));
+    GOFPID_CUDA_TRY(cudaMemset(R->count, 0, (size_t)n_streams * sizeof(int)));
+    GOFPID_CUDA_TRY(cudaMalloc(&R->n_labelled, (size_t)n_streams * sizeof(int)));
+    GOFPID_CUDA_TRY(cudaMemset(R->n_labelled, 0, (size_t)n_streams * sizeof(int)));
+    return GOFPID_OK;
+}
+void run_list_free(RunList *R)
+{
+    cudaFree(R->xs); cudaFree(R->xe); cudaFree(R->y); cudaFree(R->rowstart); cudaFree(R->rowend); cudaFree(R->count); cudaFree(R->label); cudaFree(R->byc); cudaFree(R->n_labelled);
+    memset(R, 0, sizeof(*R));
 }
 
 // labelling: runs in shared memory, tiled union-find for the streams that raised the fallback flag
 static int launch_labelling(ImageU8 mask, const uint32_t *bitimg, int bit_pitch, size_t bit_stream,
-                            int32_t *labels, size_t LP, size_t labels_stream, int32_t *comp, int max_blobs,
-                            int H, int W, int n_streams, gofpid_frame_info *info, const FrameTick *tick,
-                            int force_tiled, cudaStream_t s)
+                            const RunList &R, int32_t *labels, size_t LP, size_t labels_stream,
+                            int32_t *comp, int max_blobs, int H, int W, int n_streams,
+                            gofpid_frame_info *info, const FrameTick *tick, int force_tiled, cudaStream_t s)
 {
-    RunCclPlan P = run_ccl_plan(H);
-    const int cap = run_ccl_cap_override();
-    if (cap >= 0 && cap < P.max_runs) P.max_runs = cap & ~7;
-    if (force_tiled) P.max_runs = 0;
-    if (P.max_runs == 0) P.smem_bytes = 0; // the kernel only raises the fallback flag
+    int max_runs = R.max_runs;
+    {
+        const char *e = getenv("GOFPID_RUNS_CAP"); // tests: force the tiled fallback with a tiny capacity
+        if (e && atoi(e) >= 0 && atoi(e) < max_runs) max_runs = atoi(e) & ~7;
+    }
+    if (force_tiled) max_runs = 0;
+    if (R.max_runs > 0) {
+        runs_extract_kernel<<<dim3((H + RX_ROWS - 1) / RX_ROWS, n_streams), RX_THREADS, 0, s>>>(
+            bitimg, bit_pitch, bit_stream, R, H);
+        GOFPID_CUDA_TRY(cudaGetLastError());
+    }
     GOFPID_CUDA_TRY(cudaFuncSetAttribute(runs_ccl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)RC_SMEM_BUDGET));
-    runs_ccl_kernel<<<n_streams, RC_THREADS, P.smem_bytes, s>>>(bitimg, bit_pitch, bit_stream, labels, LP,
-                                                                labels_stream, comp, info, max_blobs,
-                                                                P.max_runs, tick, H, W);
+    runs_ccl_kernel<<<n_streams, RC_THREADS, max_runs ? run_ccl_smem(H, R.max_runs) : 0, s>>>(
+        R, labels, LP, labels_stream, comp, info, max_blobs, max_runs, tick, H, W);
     GOFPID_CUDA_TRY(cudaGetLastError());
     const dim3 tgrid((W + CCL_TW - 1) / CCL_TW, (H + CCL_TH - 1) / CCL_TH, n_streams);
     label_tiles_kernel<<<tgrid, dim3(16, CCL_TH), 0, s>>>(mask, labels, LP, labels_stream, H, W, info, 0);
@@ -1168,7 +1359,7 @@ int launch_blobs(const BlobBuffers &B, ImageU8 mask, int H, int W, int n_streams
         GOFPID_CUDA_TRY(cudaGetLastError());
         n++;
     }
-    GOFPID_TRY(launch_labelling(mask, B.bitimg, B.bit_pitch, B.bit_stream, B.labels, B.labels_pitch,
+    GOFPID_TRY(launch_labelling(mask, B.bitimg, B.bit_pitch, B.bit_stream, B.runs, B.labels, B.labels_pitch,
                                 B.labels_stream, B.comp, B.max_blobs, H, W, n_streams, B.info, tick, 0, s));
     flatten_kernel<<<pgrid, dim3(32, 8), 0, s>>>(mask, B.labels, B.labels_pitch, B.labels_stream,
                                                  B.slot, B.comp, B.info, B.max_blobs, B.bitimg,
@@ -1181,12 +1372,21 @@ int launch_blobs(const BlobBuffers &B, ImageU8 mask, int H, int W, int n_streams
                                          (int)TRACE_SMEM_BYTES));
     const dim3 cgrid(n_streams >= 64 ? 8 : (n_streams >= 8 ? 32 : 148), n_streams);
     trace_kernel<<<cgrid, TRACE_THREADS, TRACE_SMEM_BYTES, s>>>(
-        B.labels, B.labels_pitch, B.labels_stream, B.comp, B.info, B.kept, B.points, B.max_blobs,
+        B.labels, B.labels_pitch, B.labels_stream, B.runs, B.comp, B.info, B.kept, B.points, B.max_blobs,
         B.max_kept, B.max_points, B.area_min, B.bitimg, B.bit_pitch, B.bit_stream, H, W);
     GOFPID_CUDA_TRY(cudaGetLastError());
     nest_kernel<<<n_streams, 256, 0, s>>>(B.info, B.kept, B.points, B.max_kept, B.max_points, W);
     GOFPID_CUDA_TRY(cudaGetLastError());
-    if (n_launches) *n_launches = n + 7;
+    if (n_launches) *n_launches = n + (B.runs.max_runs > 0 ? 8 : 7);
+    return GOFPID_OK;
+}
+
+int launch_fill_labels(const RunList &R, int z, const gofpid_frame_info *info, int32_t *labels, size_t LP,
+                       cudaStream_t s)
+{
+    if (R.max_runs <= 0) return GOFPID_OK;
+    fill_labels_kernel<<<(R.max_runs + 7) / 8, 256, 0, s>>>(R, z, info, labels, LP);
+    GOFPID_CUDA_TRY(cudaGetLastError());
     return GOFPID_OK;
 }
 
@@ -1231,6 +1431,8 @@ int launch_ccl_only(const uint8_t *d_mask, size_t mask_pitch, int32_t *d_labels,
     int32_t *pl = nullptr, *comp = nullptr, *slot = nullptr;
     uint32_t *bits = nullptr;
     gofpid_frame_info *fi = nullptr;
+    RunList R;
+    if (run_list_alloc(&R, H, bit_pitch, 1) != GOFPID_OK) return GOFPID_ERR_CUDA;
     GOFPID_CUDA_TRY(cudaMalloc(&pm, MP * H));
     GOFPID_CUDA_TRY(cudaMalloc(&pl, LP * H * sizeof(int32_t)));
     GOFPID_CUDA_TRY(cudaMalloc(&slot, LP * H * sizeof(int32_t)));
@@ -1246,13 +1448,16 @@ int launch_ccl_only(const uint8_t *d_mask, size_t mask_pitch, int32_t *d_labels,
         }
         ImageU8 m{pm, MP, 0};
         pack_bits_kernel<<<dim3((W + 127) / 128, (H + 7) / 8, 1), dim3(32, 8), 0, s>>>(m, bits, bit_pitch, 0, H, W);
-        rc = launch_labelling(m, bits, bit_pitch, 0, pl, LP, 0, comp, max_blobs, H, W, 1, fi, nullptr, force, s);
+        rc = launch_labelling(m, bits, bit_pitch, 0, R, pl, LP, 0, comp, max_blobs, H, W, 1, fi, nullptr, force, s);
+        if (rc) break;
+        rc = launch_fill_labels(R, 0, fi, pl, LP, s);
         if (rc) break;
         rc = launch_canonical_labels(pm, MP, pl, LP, d_labels, labels_pitch_elems, H, W, s);
         if (rc) break;
         if (cudaStreamSynchronize(s) != cudaSuccess) { set_error("labelling failed: %s", cudaGetErrorString(cudaGetLastError())); rc = GOFPID_ERR_CUDA; }
     } while (0);
     cudaFree(pm); cudaFree(pl); cudaFree(slot); cudaFree(bits); cudaFree(comp); cudaFree(fi);
+    run_list_free(&R);
     return rc;
 }
 

@@ -190,7 +190,22 @@ int launch_morph(const MorphPlan &plan, ImageU8 src, ImageU8 dst, int H, int W, 
                  cudaStream_t s, uint32_t *bitimg = nullptr, int bit_pitch = 0, size_t bit_stream = 0);
 
 // blobs ------------------------------------------------------------------------
+// per-stream list of horizontal foreground runs (runs_extract_kernel -> runs_ccl_kernel)
+struct RunList {
+    uint16_t *xs, *xe, *y; // [stream][max_runs]
+    int *rowstart, *rowend; // [stream][row_pitch]: slice of the list holding each image row's runs
+    int *count;             // [stream]: runs of the current frame (reset by runs_ccl_kernel)
+    int *n_labelled;        // [stream]: runs of the frame runs_ccl_kernel labelled last
+    int32_t *label;         // [stream][max_runs]: label value (1 + first pixel index) of every run
+    uint2 *byc;             // [stream][max_runs]: the runs grouped by component (y << 16 | xs, xe)
+    int max_runs;           // capacity per stream (multiple of 8; 0: frame shape not supported)
+    int row_pitch;
+};
+int run_list_alloc(RunList *R, int H, int bit_pitch, int n_streams);
+void run_list_free(RunList *R);
+
 struct BlobBuffers {
+    RunList runs;
     int32_t *labels;      // per stream: LP*H int32 (signed: >0 fg root value, <=0 bg class)
     size_t labels_pitch;  // elements
     size_t labels_stream; // elements between streams
@@ -209,6 +224,8 @@ struct BlobBuffers {
 // bits_ready: the morphology kernel already wrote B.bitimg for this mask
 int launch_blobs(const BlobBuffers &B, ImageU8 mask, int H, int W, int n_streams,
                  const FrameTick *tick, cudaStream_t s, int *n_launches, bool bits_ready);
+int launch_fill_labels(const RunList &R, int z, const gofpid_frame_info *info, int32_t *labels, size_t LP,
+                       cudaStream_t s);
 int launch_canonical_labels(const uint8_t *mask, size_t mask_pitch, const int32_t *labels, size_t LP,
                             int32_t *out, size_t out_pitch_elems, int H, int W, cudaStream_t s);
 int launch_ccl_only(const uint8_t *d_mask, size_t mask_pitch, int32_t *d_labels,

@@ -412,7 +412,7 @@ void morph_plan_set_levels(MorphPlan *plan, const int *levels, int n_levels)
     plan->bit_tile_h = hmax > 8 ? 64 : 32;
     const size_t nw = plan->bit_hw_l + MB_TWW + plan->bit_hw_r;
     const size_t rows = plan->bit_tile_h + plan->halo_t + plan->halo_b;
-    plan->bit_smem_bytes = 3 * (size_t)n_levels * rows * nw * sizeof(uint32_t);
+    plan->bit_smem_bytes = 2 * (size_t)n_levels * rows * nw * sizeof(uint32_t);
     if (plan->bit_smem_bytes > 160 * 1024) return; // enormous halo: stay on the byte path
     plan->n_levels = n_levels;
 }
@@ -461,53 +461,106 @@ __device__ __forceinline__ uint32_t in_image_bits(const BitGeom &G, int w)
     return m;
 }
 
-template <bool DIL>
-__device__ __forceinline__ void run_op_bits(const MorphOpDev &op, const MorphRun *__restrict__ runs,
-                                            const uint32_t *A, uint32_t *T, uint32_t *B, int nl,
-                                            const BitGeom &G, int r0, int r1, uint32_t ident_next)
+// Horizontal window of a K-wide rectangle (anchor K/2), taps known at compile time.
+template <bool DIL, int K>
+__device__ __forceinline__ uint32_t row_window_k(uint32_t a, uint32_t b, uint32_t c)
 {
-    const int tid = threadIdx.x;
+    uint32_t acc = b;
+#pragma unroll
+    for (int d = 1; d <= K / 2; d++) {
+        const uint32_t l = __funnelshift_r(a, b, 32 - d); // pixel x - d
+        const uint32_t r = __funnelshift_r(b, c, d);      // pixel x + d
+        acc = DIL ? (acc | l | r) : (acc & l & r);
+    }
+    return acc;
+}
+
+constexpr int MB_R = 4; // output rows per work item (a thread owns MB_R rows of one word column)
+
+// One step on all planes: A -> B.  A work item is (plane, word column, block of MB_R rows); every
+// row of the buffer is computed (rows / bits whose support leaves the buffer come out wrong, but
+// by construction they lie in the part of the halo that later steps no longer read).
+template <bool DIL, int K>
+__device__ __forceinline__ void run_op_bits(const MorphOpDev &op, const MorphRun *__restrict__ runs,
+                                            const uint32_t *A, uint32_t *B, int nl, const BitGeom &G,
+                                            uint32_t ident_next)
+{
     const int NW = G.NW;
     const uint32_t ident = DIL ? 0u : 0xffffffffu;
-    if (op.is_rect) {
-        // row pass over the rows the column pass reads
-        const int rr0 = r0 - op.ay, nr = (r1 - r0) + op.kh - 1;
-        const int per = nr * NW;
-        for (int i = tid; i < per * nl; i += MB_THREADS) {
-            const int l = i / per, q = i - l * per;
-            const int r = rr0 + q / NW, w = q % NW;
-            const uint32_t *row = A + (size_t)l * G.plane + (size_t)r * NW;
-            const uint32_t a = w > 0 ? row[w - 1] : ident, c = w + 1 < NW ? row[w + 1] : ident;
-            T[(size_t)l * G.plane + (size_t)r * NW + w] = run_window<DIL>(a, row[w], c, -op.ax, op.kw);
-        }
-        __syncthreads();
-    }
-    {
-        const int nr = r1 - r0;
-        const int per = nr * NW;
-        for (int i = tid; i < per * nl; i += MB_THREADS) {
-            const int l = i / per, q = i - l * per;
-            const int r = r0 + q / NW, w = q % NW;
-            uint32_t acc = ident;
-            if (op.is_rect) {
-                const uint32_t *t = T + (size_t)l * G.plane + (size_t)(r - op.ay) * NW + w;
-                for (int k = 0; k < op.kh; k++) acc = DIL ? (acc | t[(size_t)k * NW]) : (acc & t[(size_t)k * NW]);
-            } else {
-                for (int qi = op.run_begin; qi < op.run_end; qi++) {
-                    const MorphRun run = runs[qi];
-                    const uint32_t *row = A + (size_t)l * G.plane + (size_t)(r + run.dy) * NW;
-                    const uint32_t a = w > 0 ? row[w - 1] : ident, c = w + 1 < NW ? row[w + 1] : ident;
-                    const uint32_t v = run_window<DIL>(a, row[w], c, run.dx, run.len);
-                    acc = DIL ? (acc | v) : (acc & v);
+    const int nrb = (G.rows + MB_R - 1) / MB_R;
+    const int nitems = nl * NW * nrb;
+    for (int item = threadIdx.x; item < nitems; item += MB_THREADS) {
+        const int w = item % NW, t = item / NW;
+        const int rb = t % nrb, l = t / nrb;
+        const uint32_t *Ap = A + (size_t)l * G.plane;
+        uint32_t *Bp = B + (size_t)l * G.plane;
+        const int r0 = rb * MB_R;
+        uint32_t acc[MB_R];
+#pragma unroll
+        for (int q = 0; q < MB_R; q++) acc[q] = ident;
+        auto load3 = [&](int rr, uint32_t &a, uint32_t &b, uint32_t &c) {
+            const uint32_t *row = Ap + (size_t)min(max(rr, 0), G.rows - 1) * NW;
+            a = w > 0 ? row[w - 1] : ident; b = row[w]; c = w + 1 < NW ? row[w + 1] : ident;
+        };
+        if (K > 0) {
+            // K x K rectangle: K + MB_R - 1 row windows, each output row is the AND / OR of K of them
+            uint32_t h[MB_R + (K > 0 ? K : 1) - 1];
+#pragma unroll
+            for (int i = 0; i < MB_R + K - 1; i++) {
+                uint32_t a, b, c;
+                load3(r0 - K / 2 + i, a, b, c);
+                h[i] = row_window_k<DIL, (K > 0 ? K : 1)>(a, b, c);
+            }
+#pragma unroll
+            for (int q = 0; q < MB_R; q++)
+#pragma unroll
+                for (int k = 0; k < K; k++) acc[q] = DIL ? (acc[q] | h[q + k]) : (acc[q] & h[q + k]);
+        } else if (op.is_rect) {
+            const int top = op.ay, bot = op.kh - 1 - op.ay;
+            for (int rr = r0 - top; rr < r0 + MB_R + bot; rr++) {
+                uint32_t a, b, c;
+                load3(rr, a, b, c);
+                const uint32_t hv = run_window<DIL>(a, b, c, -op.ax, op.kw);
+#pragma unroll
+                for (int q = 0; q < MB_R; q++)
+                    if (rr >= r0 + q - top && rr <= r0 + q + bot) acc[q] = DIL ? (acc[q] | hv) : (acc[q] & hv);
+            }
+        } else {
+            for (int qi = op.run_begin; qi < op.run_end; qi++) {
+                const MorphRun run = runs[qi];
+#pragma unroll
+                for (int q = 0; q < MB_R; q++) {
+                    uint32_t a, b, c;
+                    load3(r0 + q + run.dy, a, b, c);
+                    const uint32_t v = run_window<DIL>(a, b, c, run.dx, run.len);
+                    acc[q] = DIL ? (acc[q] | v) : (acc[q] & v);
                 }
             }
-            // cells outside the image take the identity of the NEXT step (OpenCV ignores them)
+        }
+        // cells outside the image take the identity of the NEXT step (OpenCV ignores them)
+        const uint32_t inm = in_image_bits(G, w);
+#pragma unroll
+        for (int q = 0; q < MB_R; q++) {
+            const int r = r0 + q;
+            if (r >= G.rows) break;
             const int gy = G.gy0 + r;
-            const uint32_t m = (gy >= 0 && gy < G.H) ? in_image_bits(G, w) : 0u;
-            B[(size_t)l * G.plane + (size_t)r * NW + w] = (acc & m) | (ident_next & ~m);
+            const uint32_t m = (gy >= 0 && gy < G.H) ? inm : 0u;
+            Bp[(size_t)r * NW + w] = (acc[q] & m) | (ident_next & ~m);
         }
     }
     __syncthreads();
+}
+
+template <bool DIL>
+__device__ __forceinline__ void run_op_bits_dispatch(const MorphOpDev &op, const MorphRun *__restrict__ runs,
+                                                     const uint32_t *A, uint32_t *B, int nl,
+                                                     const BitGeom &G, uint32_t ident_next)
+{
+    const bool sq = op.is_rect && op.kw == op.kh && (op.kw & 1);
+    if (sq && op.kw == 5) run_op_bits<DIL, 5>(op, runs, A, B, nl, G, ident_next);
+    else if (sq && op.kw == 3) run_op_bits<DIL, 3>(op, runs, A, B, nl, G, ident_next);
+    else if (sq && op.kw == 7) run_op_bits<DIL, 7>(op, runs, A, B, nl, G, ident_next);
+    else run_op_bits<DIL, 0>(op, runs, A, B, nl, G, ident_next);
 }
 
 __global__ void __launch_bounds__(MB_THREADS)
@@ -524,8 +577,7 @@ morph_bits_kernel(MorphPlan plan, ImageU8 src, ImageU8 dst, uint32_t *bitimg, in
     const int x0 = blockIdx.x * (MB_TWW * 32), y0 = blockIdx.y * plan.bit_tile_h;
     G.gx0 = x0 - 32 * plan.bit_hw_l; G.gy0 = y0 - plan.halo_t; G.H = H; G.W = W;
     uint32_t *A = reinterpret_cast<uint32_t *>(smem);
-    uint32_t *T = A + (size_t)nl * G.plane;
-    uint32_t *B = T + (size_t)nl * G.plane;
+    uint32_t *B = A + (size_t)nl * G.plane;
     const uint8_t *sbase = src.base + (size_t)blockIdx.z * src.stream_stride;
     uint8_t *dbase = dst.base + (size_t)blockIdx.z * dst.stream_stride;
     const bool aligned = ((reinterpret_cast<uintptr_t>(sbase) | src.pitch) & 15) == 0;
@@ -571,14 +623,12 @@ morph_bits_kernel(MorphPlan plan, ImageU8 src, ImageU8 dst, uint32_t *bitimg, in
 
     const int tile_h = plan.bit_tile_h;
     if (nonempty) {
-        int r0 = 0, r1 = G.rows;
         for (int k = 0; k < plan.n_ops; k++) {
             const MorphOpDev &op = plan.ops[k];
-            r0 += op.ay; r1 -= op.kh - 1 - op.ay;
             const uint32_t ident_next =
                 (k + 1 < plan.n_ops && plan.ops[k + 1].op == GOFPID_MORPH_ERODE) ? 0xffffffffu : 0u;
-            if (op.op == GOFPID_MORPH_DILATE) run_op_bits<true>(op, plan.d_runs, A, T, B, nl, G, r0, r1, ident_next);
-            else run_op_bits<false>(op, plan.d_runs, A, T, B, nl, G, r0, r1, ident_next);
+            if (op.op == GOFPID_MORPH_DILATE) run_op_bits_dispatch<true>(op, plan.d_runs, A, B, nl, G, ident_next);
+            else run_op_bits_dispatch<false>(op, plan.d_runs, A, B, nl, G, ident_next);
             uint32_t *t = A; A = B; B = t;
         }
     }

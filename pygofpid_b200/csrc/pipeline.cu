@@ -191,6 +191,7 @@ void free_all(gofpid_pipeline *p)
     morph_plan_destroy(&p->morph);
     for (auto &S : p->slots) {
         cudaFree(S.d_final);
+        run_list_free(&S.blobs.runs);
         cudaFree(S.blobs.labels); cudaFree(S.blobs.slot); cudaFree(S.blobs.comp); cudaFree(S.blobs.bitimg);
         cudaFree(S.blobs.info); cudaFree(S.blobs.kept); cudaFree(S.blobs.points);
         cudaFree(S.d_frames);
@@ -331,6 +332,7 @@ int build(gofpid_pipeline *p)
         B.bit_pitch = (int)round_up((size_t)(W + 31) / 32 + 2, 4);
         B.bit_stream = (size_t)B.bit_pitch * (H + 2);
         GOFPID_TRY(alloc_zero((void **)&B.bitimg, B.bit_stream * sizeof(uint32_t) * S));
+        GOFPID_TRY(run_list_alloc(&B.runs, H, B.bit_pitch, S));
         GOFPID_TRY(alloc_zero((void **)&B.comp, (size_t)B.max_blobs * 8 * sizeof(int32_t) * S));
         GOFPID_TRY(alloc_zero((void **)&B.info, sizeof(gofpid_frame_info) * S));
         GOFPID_TRY(alloc_zero((void **)&B.kept, sizeof(gofpid_blob) * B.max_kept * S));
@@ -811,7 +813,11 @@ GOFPID_API int gofpid_pipeline_labels(gofpid_pipeline *p, int stream_idx, int32_
         out = tmp; out_pitch = p->W;
     }
     const BlobBuffers &B = F->blobs;
-    int rc = launch_canonical_labels(F->d_final + (size_t)stream_idx * p->mask_stream, p->mask_pitch,
+    // (the hot path labels runs, not pixels: the label image is filled in here, on demand)
+    int rc = launch_fill_labels(B.runs, stream_idx, B.info + stream_idx,
+                                B.labels + (size_t)stream_idx * B.labels_stream, B.labels_pitch, s);
+    if (rc == GOFPID_OK)
+        rc = launch_canonical_labels(F->d_final + (size_t)stream_idx * p->mask_stream, p->mask_pitch,
                                      B.labels + (size_t)stream_idx * B.labels_stream, B.labels_pitch, out,
                                      out_pitch, p->H, p->W, s);
     if (rc == GOFPID_OK && !dst_is_device) {
@@ -1019,12 +1025,16 @@ GOFPID_API int gofpid_morph_levels_u8(const uint8_t *d_src, size_t src_pitch, ui
     MorphPlan plan;
     GOFPID_TRY(morph_plan_create(ops, n_ops, &plan));
     if (levels && n_levels > 0) {
-        morph_plan_set_levels(&plan, levels, n_levels);
-        if (n_ops > 0 && plan.n_levels == 0) {
+        bool ok = n_levels <= 3;
+        for (int i = 0; ok && i < n_levels; i++)
+            ok = levels[i] >= 1 && levels[i] <= 255 && (i == 0 || levels[i] > levels[i - 1]);
+        if (!ok) {
             morph_plan_destroy(&plan);
             set_error("levels must be 1..3 ascending values in [1, 255]");
             return GOFPID_ERR_INVALID;
         }
+        // (a chain the bit-plane kernel declines -- see morph_plan_set_levels -- stays on the byte kernel)
+        morph_plan_set_levels(&plan, levels, n_levels);
     }
     int rc = launch_morph(plan, ImageU8{const_cast<uint8_t *>(d_src), src_pitch, 0}, ImageU8{d_dst, dst_pitch, 0},
                           H, W, 1, (cudaStream_t)stream);

@@ -25,7 +25,8 @@ def main(path):
     print("%-40s %5s %12s %8s" % ("kernel", "n", "mean_us", "share"))
     for k, v in sorted(agg.items(), key=lambda kv: -sum(kv[1])):
         print("%-40s %5d %12.2f %7.1f%%" % (k[:40], len(v), sum(v) / len(v), 100 * sum(v) / tot))
-    print("total per frame (us): %.1f" % (tot / max(len(v) for v in agg.values())))
+    if agg:
+        print("total per frame (us): %.1f" % (tot / max(len(v) for v in agg.values())))
 
 
 if __name__ == "__main__":
