@@ -279,8 +279,8 @@ def main():
 
     # ---- timed: end to end through the host entry points (pinned frames in, blob lists out) ----
     # Every frame is copied host->device inside the timed region and its blob list is read back
-    # to the host; frame t+1 is submitted before frame t's results are collected (two frames in
-    # flight, the library's pipelined host API: submit_host / select / blobs).
+    # to the host; frames t+1 and t+2 are submitted before frame t's results are collected (three
+    # frames in flight, the library's pipelined host API: submit_host / select / blobs).
     e2e_frames = F * max(1, args.steps // 4)
     for i in range(4):  # untimed: first use of the host path allocates its staging buffers
         hp.process_pinned(pinned[(t_idx + i) % n_clip].data_ptr(), row, frame_bytes)
@@ -289,12 +289,13 @@ def main():
     w0 = time.perf_counter()
     d2h = 0
     nblobs = 0
-    for i in range(e2e_frames + 1):
+    LAG = 2  # frames submitted ahead of the one whose results are collected (3 frames in flight)
+    for i in range(e2e_frames + LAG):
         if i < e2e_frames:
             t = (t_idx + i) % n_clip
             hp.submit_pinned(pinned[t].data_ptr(), row, frame_bytes)
-        if i > 0:
-            hp.select(1 if i < e2e_frames else 0)
+        if i >= LAG:
+            hp.select(min(i, e2e_frames - 1) - (i - LAG))
             for z in range(S):
                 recs, pts = hp.raw_blobs(z)
                 nblobs += len(recs)
@@ -357,7 +358,7 @@ def main():
                     "mpix_per_s": e2e_fps * mpix,
                     "blobs_per_frame": nblobs / max(e2e_frames * S, 1),
                     "api": "gofpid_pipeline_submit_host + gofpid_pipeline_select + gofpid_pipeline_blobs "
-                           "(pinned host frames in, blob lists with contours out, 2 frames in flight)"},
+                           "(pinned host frames in, blob lists with contours out, 3 frames in flight)"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic_per_launch(kname),

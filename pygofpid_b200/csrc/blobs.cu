@@ -259,7 +259,8 @@ __device__ long long g_rc_dbg[16];
 
 __global__ void __launch_bounds__(RC_THREADS, 1)
 runs_ccl_kernel(RunList R, int32_t *labels, size_t LP, size_t labels_stream, int32_t *comp,
-                gofpid_frame_info *info, int max_blobs, int max_runs, const FrameTick *tick, int H, int W)
+                gofpid_frame_info *info, int max_blobs, int max_runs, const FrameTick *tick, int H, int W,
+                cudaGraphConditionalHandle cond, int use_cond)
 {
     extern __shared__ __align__(16) unsigned char rsm[];
     const int z = blockIdx.x;
@@ -285,6 +286,8 @@ runs_ccl_kernel(RunList R, int32_t *labels, size_t LP, size_t labels_stream, int
         fi->n_components = 0; fi->n_candidates = 0; fi->n_kept = 0; fi->n_points = 0;
         fi->overflow = 0; fi->frame_index = tick ? tick->nframes : 0;
         fi->reserved[0] = 0; fi->reserved[1] = fallback ? 1 : 0;
+        // inside a captured step the tiled fallback kernels sit in a conditional graph node
+        if (fallback && use_cond) cudaGraphSetConditional(cond, 1);
     }
     if (fallback) return;
 
@@ -373,7 +376,10 @@ runs_ccl_kernel(RunList R, int32_t *labels, size_t LP, size_t labels_stream, int
     __syncthreads();
     const int ncomp = sh_scan[31];
     if (ncomp > RC_MAX_COMP && ncomp <= max_blobs) { // more components than slots here: tiled path
-        if (tid == 0) fi->reserved[1] = 1;
+        if (tid == 0) {
+            fi->reserved[1] = 1;
+            if (use_cond) cudaGraphSetConditional(cond, 1);
+        }
         return;
     }
     const int nslot = min(ncomp, min(max_blobs, RC_MAX_COMP));
@@ -400,17 +406,31 @@ runs_ccl_kernel(RunList R, int32_t *labels, size_t LP, size_t labels_stream, int
     // ---- E: component statistics; every run learns its slot -------------------------------------
     // (bands land in the run list in any order, so the smallest index is not the raster-first run:
     // the first pixel is the minimum of y * LP + xs over the component)
-    for (int k = tid; k < N; k += RC_THREADS) {
-        int p = parent[k];
-        if (p >= 0) p = parent[p];
-        const int slot = -p - 1;
-        if (slot >= nslot) continue; // beyond the handle's capacity (overflow is flagged below)
-        const int xs = run_xs[k], xe = run_xe[k], y = run_y[k];
-        atomicMin(&c_first[slot], (int)((size_t)y * LP + xs));
-        atomicAdd(&c_area[slot], xe - xs + 1);
-        atomicAdd(&c_nruns[slot], 1);
-        atomicMin(&c_x0[slot], xs); atomicMax(&c_x1[slot], xe);
-        atomicMin(&c_y0[slot], y); atomicMax(&c_y1[slot], y);
+    for (int kb = 0; kb < N; kb += RC_THREADS) {
+        const int k = kb + tid;
+        int slot = -1, xs = 0, xe = 0, y = 0;
+        if (k < N) {
+            int p = parent[k];
+            if (p >= 0) p = parent[p];
+            slot = -p - 1;
+            if (slot >= nslot) slot = -1; // beyond the handle's capacity (overflow is flagged below)
+            xs = run_xs[k]; xe = run_xe[k]; y = run_y[k];
+        }
+        // neighbouring runs mostly belong to a handful of components: one atomic set per warp and component
+        const unsigned grp = __match_any_sync(0xffffffffu, slot);
+        if (slot >= 0) {
+            const int first = __reduce_min_sync(grp, (int)((size_t)y * LP + xs));
+            const int area = __reduce_add_sync(grp, xe - xs + 1);
+            const int mnx = __reduce_min_sync(grp, xs), mxx = __reduce_max_sync(grp, xe);
+            const int mny = __reduce_min_sync(grp, y), mxy = __reduce_max_sync(grp, y);
+            if (lane == __ffs(grp) - 1) {
+                atomicMin(&c_first[slot], first);
+                atomicAdd(&c_area[slot], area);
+                atomicAdd(&c_nruns[slot], __popc(grp));
+                atomicMin(&c_x0[slot], mnx); atomicMax(&c_x1[slot], mxx);
+                atomicMin(&c_y0[slot], mny); atomicMax(&c_y1[slot], mxy);
+            }
+        }
     }
     __syncthreads();
     RC_T(6);
@@ -893,8 +913,7 @@ trace_kernel(const int32_t *labels, size_t LP, size_t labels_stream, RunList R, 
     int *nxtB = nxtA + TRACE_MAX_CP;
     unsigned *dA = reinterpret_cast<unsigned *>(nxtB + TRACE_MAX_CP);
     unsigned *dB = dA + TRACE_MAX_CP;
-    __shared__ int sh_ncp, sh_keep, sh_off;
-    __shared__ int sh_warp[32];
+    __shared__ int sh_ncp, sh_ncand, sh_keep, sh_off;
     __shared__ long long sh_part[3][32];
     const int z = blockIdx.y;
     const int32_t *lab = labels + (size_t)z * labels_stream;
@@ -960,29 +979,6 @@ trace_kernel(const int32_t *labels, size_t LP, size_t labels_stream, RunList R, 
         // (C) the states are written to their slots and entered in the hash table.
         int *cand_list = nxtA; // the ranking arrays are free until pass 1: 4 * TRACE_MAX_CP ints
         constexpr int CAND_CAP = 4 * TRACE_MAX_CP;
-        auto block_scan = [&](int mine, int &total) -> int { // exclusive prefix of `mine`
-            int incl = mine;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const int t = __shfl_up_sync(0xffffffffu, incl, o);
-                if ((tid & 31) >= o) incl += t;
-            }
-            __syncthreads(); // sh_warp may still be read from the previous scan
-            if ((tid & 31) == 31) sh_warp[tid >> 5] = incl;
-            __syncthreads();
-            if (tid < 32) {
-                int v = tid < TRACE_THREADS / 32 ? sh_warp[tid] : 0;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) {
-                    const int t = __shfl_up_sync(0xffffffffu, v, o);
-                    if (tid >= o) v += t;
-                }
-                sh_warp[tid] = v; // inclusive totals per warp
-            }
-            __syncthreads();
-            total = sh_warp[31];
-            return ((tid >> 5) ? sh_warp[(tid >> 5) - 1] : 0) + incl - mine;
-        };
         // hash-selected border pixels of bit-image word wc of image row y, columns [xlo, xhi]
         auto cands_at = [&](int y, int wc, int xlo, int xhi) -> uint32_t {
             const int xw = (wc << 5) - 32;
@@ -1013,10 +1009,11 @@ trace_kernel(const int32_t *labels, size_t LP, size_t labels_stream, RunList R, 
         const int nruns = by_runs ? cr[CR_NRUNS] : 0;
         auto for_each_word = [&](auto &&f) {
             if (by_runs) {
-                for (int i = tid; i < nruns; i += TRACE_THREADS) {
+                // eight lanes share a run (256 pixels per round), 128 runs in flight per CTA
+                for (int i = tid >> 3; i < nruns; i += TRACE_THREADS / 8) {
                     const uint2 rr = __ldg(cruns + i);
                     const int y = (int)(rr.x >> 16), xs_ = (int)(rr.x & 0xffffu), xe_ = (int)rr.y;
-                    for (int wc = (xs_ + 32) >> 5; wc <= (xe_ + 32) >> 5; wc++) f(y, wc, xs_, xe_);
+                    for (int wc = ((xs_ + 32) >> 5) + (tid & 7); wc <= (xe_ + 32) >> 5; wc += 8) f(y, wc, xs_, xe_);
                 }
             } else {
                 for (int i = tid; i < wpr * bh; i += TRACE_THREADS) {
@@ -1036,47 +1033,46 @@ trace_kernel(const int32_t *labels, size_t LP, size_t labels_stream, RunList R, 
             if (x == xs && y == ys) starts &= ~(1u << b0); // that one is checkpoint 0
             return starts;
         };
+        // Two phases, slots handed out by shared-memory counters (the order of candidates and
+        // checkpoints is irrelevant: the hash table maps a visit state to its id and the ranking
+        // below orders the segments): (A) the hash-selected border pixels go to a candidate list;
+        // (B) one thread per candidate enters its visit states in the checkpoint table.
         while (true) {
             for (int i = tid; i < TRACE_HT; i += TRACE_THREADS) ht_keys[i] = 0;
-            // ---- A: candidate pixels ------------------------------------------------------
-            int mine = 0;
-            for_each_word([&](int y, int wc, int xlo, int xhi) { mine += __popc(cands_at(y, wc, xlo, xhi)); });
-            int ncand;
-            int slot = block_scan(mine, ncand);
+            if (tid == 0) { sh_ncand = 0; sh_ncp = 1; } // checkpoint 0 is the start state
+            __syncthreads();
+            for_each_word([&](int y, int wc, int xlo, int xhi) {
+                const uint32_t c = cands_at(y, wc, xlo, xhi);
+                if (c) {
+                    int pos = atomicAdd(&sh_ncand, __popc(c));
+                    for (uint32_t m = c; m; m &= m - 1, pos++)
+                        if (pos < CAND_CAP) cand_list[pos] = (y << 16) | ((wc << 5) - 32 + __ffs(m) - 1);
+                }
+            });
+            __syncthreads();
+            const int ncand = sh_ncand;
             bool retry = ncand > CAND_CAP;
-            int nstates = 0;
             if (!retry) {
-                for_each_word([&](int y, int wc, int xlo, int xhi) {
-                    for (uint32_t m = cands_at(y, wc, xlo, xhi); m; m &= m - 1)
-                        cand_list[slot++] = (y << 16) | ((wc << 5) - 32 + __ffs(m) - 1);
-                });
-                __syncthreads();
-                // ---- B: states per candidate ----------------------------------------------
-                mine = 0;
-                for (int k = tid; k < ncand; k += TRACE_THREADS)
-                    mine += __popc(visit_states(cand_list[k] & 0xffff, cand_list[k] >> 16));
-                slot = 1 + block_scan(mine, nstates);
-                retry = nstates + 1 > TRACE_MAX_CP;
-            }
-            if (!retry) {
-                // ---- C: fill -------------------------------------------------------------------
                 if (tid == 0) {
-                    sh_ncp = nstates + 1;
                     cp_state[0] = (ys << 16) | (xs << 3) | b0;
                     ht_insert(ht_keys, ht_vals, cp_key(xs, ys, b0), 0);
                 }
                 for (int k = tid; k < ncand; k += TRACE_THREADS) {
                     const int x = cand_list[k] & 0xffff, y = cand_list[k] >> 16;
-                    for (unsigned st = visit_states(x, y); st; st &= st - 1) {
-                        const int b = __ffs(st) - 1;
-                        cp_state[slot] = (y << 16) | (x << 3) | b;
-                        ht_insert(ht_keys, ht_vals, cp_key(x, y, b), slot);
-                        slot++;
+                    const unsigned st0 = visit_states(x, y);
+                    if (!st0) continue;
+                    int slot = atomicAdd(&sh_ncp, __popc(st0));
+                    for (unsigned st = st0; st; st &= st - 1, slot++) {
+                        if (slot >= TRACE_MAX_CP) break;
+                        const int bdir = __ffs(st) - 1;
+                        cp_state[slot] = (y << 16) | (x << 3) | bdir;
+                        ht_insert(ht_keys, ht_vals, cp_key(x, y, bdir), slot);
                     }
                 }
                 __syncthreads();
-                break;
+                retry = sh_ncp > TRACE_MAX_CP;
             }
+            if (!retry) break;
             rmask = (rmask << 1) | 1u; // too many: halve the density and start over
             __syncthreads();
         }
@@ -1319,11 +1315,12 @@ void run_list_free(RunList *R)
     memset(R, 0, sizeof(*R));
 }
 
-// labelling: runs in shared memory, tiled union-find for the streams that raised the fallback flag
+// run-based labelling in shared memory; streams that do not fit raise their fallback flag
 static int launch_labelling(ImageU8 mask, const uint32_t *bitimg, int bit_pitch, size_t bit_stream,
                             const RunList &R, int32_t *labels, size_t LP, size_t labels_stream,
                             int32_t *comp, int max_blobs, int H, int W, int n_streams,
-                            gofpid_frame_info *info, const FrameTick *tick, int force_tiled, cudaStream_t s)
+                            gofpid_frame_info *info, const FrameTick *tick, int force_tiled, cudaStream_t s,
+                            const cudaGraphConditionalHandle *cond)
 {
     int max_runs = R.max_runs;
     {
@@ -1339,18 +1336,41 @@ static int launch_labelling(ImageU8 mask, const uint32_t *bitimg, int bit_pitch,
     GOFPID_CUDA_TRY(cudaFuncSetAttribute(runs_ccl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)RC_SMEM_BUDGET));
     runs_ccl_kernel<<<n_streams, RC_THREADS, max_runs ? run_ccl_smem(H, R.max_runs) : 0, s>>>(
-        R, labels, LP, labels_stream, comp, info, max_blobs, max_runs, tick, H, W);
+        R, labels, LP, labels_stream, comp, info, max_blobs, max_runs, tick, H, W, cond ? *cond : 0, cond ? 1 : 0);
     GOFPID_CUDA_TRY(cudaGetLastError());
+    return GOFPID_OK;
+}
+
+// tiled labelling of the streams that raised the fallback flag (all of them with force = 1)
+static int launch_tiled_labelling(ImageU8 mask, int32_t *labels, size_t LP, size_t labels_stream, int H, int W,
+                                  int n_streams, gofpid_frame_info *info, int force, cudaStream_t s)
+{
     const dim3 tgrid((W + CCL_TW - 1) / CCL_TW, (H + CCL_TH - 1) / CCL_TH, n_streams);
-    label_tiles_kernel<<<tgrid, dim3(16, CCL_TH), 0, s>>>(mask, labels, LP, labels_stream, H, W, info, 0);
+    label_tiles_kernel<<<tgrid, dim3(16, CCL_TH), 0, s>>>(mask, labels, LP, labels_stream, H, W, info, force);
     GOFPID_CUDA_TRY(cudaGetLastError());
-    merge_tiles_kernel<<<tgrid, CCL_TW + 2 * CCL_TH, 0, s>>>(mask, labels, LP, labels_stream, H, W, info, 0);
+    merge_tiles_kernel<<<tgrid, CCL_TW + 2 * CCL_TH, 0, s>>>(mask, labels, LP, labels_stream, H, W, info, force);
+    GOFPID_CUDA_TRY(cudaGetLastError());
+    return GOFPID_OK;
+}
+
+// the tiled fallback: labelling, flatten + slots, statistics
+static int launch_fallback(const BlobBuffers &B, ImageU8 mask, int H, int W, int n_streams, cudaStream_t s)
+{
+    GOFPID_TRY(launch_tiled_labelling(mask, B.labels, B.labels_pitch, B.labels_stream, H, W, n_streams, B.info, 0, s));
+    const dim3 pgrid((W + 127) / 128, (H + 7) / 8, n_streams);
+    flatten_kernel<<<pgrid, dim3(32, 8), 0, s>>>(mask, B.labels, B.labels_pitch, B.labels_stream,
+                                                 B.slot, B.comp, B.info, B.max_blobs, B.bitimg,
+                                                 B.bit_pitch, B.bit_stream, H, W);
+    GOFPID_CUDA_TRY(cudaGetLastError());
+    stats_kernel<<<pgrid, dim3(32, 8), 0, s>>>(mask, B.labels, B.labels_pitch, B.labels_stream,
+                                               B.slot, B.comp, B.info, B.max_blobs, H, W);
     GOFPID_CUDA_TRY(cudaGetLastError());
     return GOFPID_OK;
 }
 
 int launch_blobs(const BlobBuffers &B, ImageU8 mask, int H, int W, int n_streams,
-                 const FrameTick *tick, cudaStream_t s, int *n_launches, bool bits_ready)
+                 const FrameTick *tick, cudaStream_t s, int *n_launches, bool bits_ready,
+                 const cudaGraphConditionalHandle *cond)
 {
     int n = 0;
     const dim3 pgrid((W + 127) / 128, (H + 7) / 8, n_streams);
@@ -1360,14 +1380,41 @@ int launch_blobs(const BlobBuffers &B, ImageU8 mask, int H, int W, int n_streams
         n++;
     }
     GOFPID_TRY(launch_labelling(mask, B.bitimg, B.bit_pitch, B.bit_stream, B.runs, B.labels, B.labels_pitch,
-                                B.labels_stream, B.comp, B.max_blobs, H, W, n_streams, B.info, tick, 0, s));
-    flatten_kernel<<<pgrid, dim3(32, 8), 0, s>>>(mask, B.labels, B.labels_pitch, B.labels_stream,
-                                                 B.slot, B.comp, B.info, B.max_blobs, B.bitimg,
-                                                 B.bit_pitch, B.bit_stream, H, W);
-    GOFPID_CUDA_TRY(cudaGetLastError());
-    stats_kernel<<<pgrid, dim3(32, 8), 0, s>>>(mask, B.labels, B.labels_pitch, B.labels_stream,
-                                               B.slot, B.comp, B.info, B.max_blobs, H, W);
-    GOFPID_CUDA_TRY(cudaGetLastError());
+                                B.labels_stream, B.comp, B.max_blobs, H, W, n_streams, B.info, tick, 0, s, cond));
+    if (cond) {
+        // `s` is being captured: the fallback kernels go into the body of an IF node whose condition
+        // runs_ccl_kernel raises, so a normal frame does not even launch them
+        cudaStreamCaptureStatus st;
+        cudaGraph_t g = nullptr;
+        const cudaGraphNode_t *deps = nullptr;
+        size_t nd = 0;
+        GOFPID_CUDA_TRY(cudaStreamGetCaptureInfo(s, &st, nullptr, &g, &deps, &nd));
+        if (st != cudaStreamCaptureStatusActive || !g) { set_error("internal: stage B is not being captured"); return GOFPID_ERR_CUDA; }
+        cudaGraphNodeParams cp = {};
+        cp.type = cudaGraphNodeTypeConditional;
+        cp.conditional.handle = *cond;
+        cp.conditional.type = cudaGraphCondTypeIf;
+        cp.conditional.size = 1;
+        cudaGraphNode_t cn;
+        GOFPID_CUDA_TRY(cudaGraphAddNode(&cn, g, deps, nd, &cp));
+        cudaGraph_t body = cp.conditional.phGraph_out[0];
+        GOFPID_CUDA_TRY(cudaStreamUpdateCaptureDependencies(s, &cn, 1, cudaStreamSetCaptureDependencies));
+        cudaStream_t aux;
+        GOFPID_CUDA_TRY(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
+        cudaError_t e = cudaStreamBeginCaptureToGraph(aux, body, nullptr, nullptr, 0, cudaStreamCaptureModeThreadLocal);
+        int rc = GOFPID_OK;
+        if (e == cudaSuccess) {
+            rc = launch_fallback(B, mask, H, W, n_streams, aux);
+            cudaGraph_t tmp = nullptr;
+            e = cudaStreamEndCapture(aux, &tmp);
+        }
+        cudaStreamDestroy(aux);
+        if (rc != GOFPID_OK) return rc;
+        if (e != cudaSuccess) { set_error("capturing the fallback body failed: %s", cudaGetErrorString(e)); return GOFPID_ERR_CUDA; }
+    } else {
+        GOFPID_TRY(launch_fallback(B, mask, H, W, n_streams, s));
+        n += 4;
+    }
     GOFPID_CUDA_TRY(cudaFuncSetAttribute(trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                          (int)TRACE_SMEM_BYTES));
     const dim3 cgrid(n_streams >= 64 ? 8 : (n_streams >= 8 ? 32 : 148), n_streams);
@@ -1377,7 +1424,7 @@ int launch_blobs(const BlobBuffers &B, ImageU8 mask, int H, int W, int n_streams
     GOFPID_CUDA_TRY(cudaGetLastError());
     nest_kernel<<<n_streams, 256, 0, s>>>(B.info, B.kept, B.points, B.max_kept, B.max_points, W);
     GOFPID_CUDA_TRY(cudaGetLastError());
-    if (n_launches) *n_launches = n + (B.runs.max_runs > 0 ? 8 : 7);
+    if (n_launches) *n_launches = n + (B.runs.max_runs > 0 ? 4 : 3);
     return GOFPID_OK;
 }
 
@@ -1448,7 +1495,9 @@ int launch_ccl_only(const uint8_t *d_mask, size_t mask_pitch, int32_t *d_labels,
         }
         ImageU8 m{pm, MP, 0};
         pack_bits_kernel<<<dim3((W + 127) / 128, (H + 7) / 8, 1), dim3(32, 8), 0, s>>>(m, bits, bit_pitch, 0, H, W);
-        rc = launch_labelling(m, bits, bit_pitch, 0, R, pl, LP, 0, comp, max_blobs, H, W, 1, fi, nullptr, force, s);
+        rc = launch_labelling(m, bits, bit_pitch, 0, R, pl, LP, 0, comp, max_blobs, H, W, 1, fi, nullptr, force, s, nullptr);
+        if (rc) break;
+        rc = launch_tiled_labelling(m, pl, LP, 0, H, W, 1, fi, 0, s);
         if (rc) break;
         rc = launch_fill_labels(R, 0, fi, pl, LP, s);
         if (rc) break;

@@ -223,7 +223,8 @@ struct BlobBuffers {
 };
 // bits_ready: the morphology kernel already wrote B.bitimg for this mask
 int launch_blobs(const BlobBuffers &B, ImageU8 mask, int H, int W, int n_streams,
-                 const FrameTick *tick, cudaStream_t s, int *n_launches, bool bits_ready);
+                 const FrameTick *tick, cudaStream_t s, int *n_launches, bool bits_ready,
+                 const cudaGraphConditionalHandle *cond = nullptr);
 int launch_fill_labels(const RunList &R, int z, const gofpid_frame_info *info, int32_t *labels, size_t LP,
                        cudaStream_t s);
 int launch_canonical_labels(const uint8_t *mask, size_t mask_pitch, const int32_t *labels, size_t LP,

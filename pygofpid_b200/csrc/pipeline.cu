@@ -30,11 +30,13 @@ void set_error(const char *fmt, ...)
 
 using namespace gofpid;
 
-// Two frames are in flight at most: stage A (tick, blur+detect, morphology) of frame t+1 runs
-// on the caller's stream while stage B (labelling, statistics, border tracing) of frame t runs
-// on an internal stream.  The temporal model makes stage A strictly sequential; stage B only
-// needs the finished mask of its own frame, so consecutive frames of ONE camera stream overlap.
-constexpr int DEPTH = 2;
+// Up to DEPTH frames are in flight: stage A (tick, blur+detect, morphology) of frame t+1 runs on
+// the caller's stream while stage B (run extraction, labelling, border tracing) of frames t and
+// t-1 runs on the internal streams of their slots.  The temporal model makes stage A strictly
+// sequential; stage B only needs the finished mask of its own frame and occupies a handful of
+// SMs (one CTA per stream or per blob), so consecutive frames of ONE camera stream overlap and
+// the frame rate is set by stage A alone.
+constexpr int DEPTH = 3;
 
 struct FrameSlot {
     uint8_t *d_final = nullptr;   // final mask of the frame in this slot
@@ -51,6 +53,7 @@ struct FrameSlot {
     cudaGraph_t graph_a = nullptr, graph_b = nullptr;
     cudaGraphExec_t exec_a = nullptr, exec_b = nullptr;
     cudaGraphNode_t tick_node = nullptr;
+    cudaGraphConditionalHandle cond_b = 0; // raised by runs_ccl_kernel: run the tiled labelling fallback
 };
 
 struct gofpid_pipeline {
@@ -58,7 +61,7 @@ struct gofpid_pipeline {
     std::vector<std::vector<uint8_t>> se_copies;
     int H = 0, W = 0, C = 0, n_streams = 0, device = 0;
     cudaStream_t stream = nullptr;   // own stage-A stream (host entry points)
-    cudaStream_t stream_b = nullptr; // stage B
+    cudaStream_t stream_b[DEPTH] = {}; // stage B, one per frame slot
     cudaStream_t stream_c = nullptr; // result fetches
     cudaStream_t stream_h = nullptr; // host->device frame copies
     BlurParams blur;
@@ -208,7 +211,9 @@ void free_all(gofpid_pipeline *p)
     }
     if (p->h_frames) cudaFreeHost(p->h_frames);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
-    for (cudaStream_t s : {p->stream, p->stream_b, p->stream_c, p->stream_h})
+    for (cudaStream_t s : {p->stream, p->stream_c, p->stream_h})
+        if (s) cudaStreamDestroy(s);
+    for (cudaStream_t s : p->stream_b)
         if (s) cudaStreamDestroy(s);
 }
 
@@ -216,8 +221,9 @@ int build(gofpid_pipeline *p)
 {
     const gofpid_config &cfg = p->cfg;
     const int H = p->H, W = p->W, C = p->C, S = p->n_streams;
-    for (cudaStream_t *s : {&p->stream, &p->stream_b, &p->stream_c, &p->stream_h})
+    for (cudaStream_t *s : {&p->stream, &p->stream_c, &p->stream_h})
         GOFPID_CUDA_TRY(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking));
+    for (cudaStream_t &s : p->stream_b) GOFPID_CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
     for (auto &e : p->ev) GOFPID_CUDA_TRY(cudaEventCreate(&e));
     GOFPID_TRY(make_blur_params(cfg.blur_kind, cfg.blur_kw, cfg.blur_kh, cfg.blur_sigma, &p->blur));
 
@@ -377,12 +383,13 @@ int enqueue_stage_a(gofpid_pipeline *p, FrameSlot &F, const FrameSrc &src, cudaS
 }
 
 // ---- stage B: labelling, statistics, border tracing on the slot's final mask ---------------------
-int enqueue_stage_b(gofpid_pipeline *p, FrameSlot &F, cudaStream_t s, int *n_launches)
+int enqueue_stage_b(gofpid_pipeline *p, FrameSlot &F, cudaStream_t s, int *n_launches,
+                    const cudaGraphConditionalHandle *cond = nullptr)
 {
     int nb = 0;
     if (p->cfg.find_blobs)
         GOFPID_TRY(launch_blobs(F.blobs, ImageU8{F.d_final, p->mask_pitch, p->mask_stream}, p->H, p->W,
-                                p->n_streams, nullptr, s, &nb, p->cfg.n_morph > 0 && p->morph.n_levels > 0));
+                                p->n_streams, nullptr, s, &nb, p->cfg.n_morph > 0 && p->morph.n_levels > 0, cond));
     if (n_launches) *n_launches = nb;
     return GOFPID_OK;
 }
@@ -412,9 +419,17 @@ int build_graphs(gofpid_pipeline *p, FrameSlot &F, const FrameSrc &src)
     if (!F.tick_node) { set_error("graph capture: tick node not found"); return GOFPID_ERR_CUDA; }
     GOFPID_CUDA_TRY(cudaGraphInstantiate(&F.exec_a, F.graph_a, 0));
     if (p->cfg.find_blobs) {
-        GOFPID_CUDA_TRY(cudaStreamBeginCapture(p->stream_b, cudaStreamCaptureModeThreadLocal));
-        rc = enqueue_stage_b(p, F, p->stream_b, &lb);
-        e = cudaStreamEndCapture(p->stream_b, &F.graph_b);
+        const char *nc = getenv("GOFPID_NO_COND");
+        const bool use_cond = !(nc && nc[0] == '1');
+        GOFPID_CUDA_TRY(cudaGraphCreate(&F.graph_b, 0));
+        if (use_cond)
+            GOFPID_CUDA_TRY(cudaGraphConditionalHandleCreate(&F.cond_b, F.graph_b, 0, cudaGraphCondAssignDefault));
+        cudaStream_t sb = p->stream_b[&F - p->slots];
+        GOFPID_CUDA_TRY(cudaStreamBeginCaptureToGraph(sb, F.graph_b, nullptr, nullptr, 0,
+                                                      cudaStreamCaptureModeThreadLocal));
+        rc = enqueue_stage_b(p, F, sb, &lb, use_cond ? &F.cond_b : nullptr);
+        cudaGraph_t captured = nullptr;
+        e = cudaStreamEndCapture(sb, &captured);
         if (rc != GOFPID_OK) return rc;
         if (e != cudaSuccess) { set_error("graph capture (stage B) failed: %s", cudaGetErrorString(e)); return GOFPID_ERR_CUDA; }
         GOFPID_CUDA_TRY(cudaGraphInstantiate(&F.exec_b, F.graph_b, 0));
@@ -459,10 +474,11 @@ int run_step(gofpid_pipeline *p, const uint8_t *d_frames, size_t pitch, size_t s
         }
         GOFPID_CUDA_TRY(cudaEventRecord(F.ev_mask, s));
         if (p->cfg.find_blobs) {
-            GOFPID_CUDA_TRY(cudaStreamWaitEvent(p->stream_b, F.ev_mask, 0));
-            if (graph) GOFPID_CUDA_TRY(cudaGraphLaunch(F.exec_b, p->stream_b));
-            else GOFPID_TRY(enqueue_stage_b(p, F, p->stream_b, &lb));
-            GOFPID_CUDA_TRY(cudaEventRecord(F.ev_blobs, p->stream_b));
+            cudaStream_t sb = p->stream_b[&F - p->slots];
+            GOFPID_CUDA_TRY(cudaStreamWaitEvent(sb, F.ev_mask, 0));
+            if (graph) GOFPID_CUDA_TRY(cudaGraphLaunch(F.exec_b, sb));
+            else GOFPID_TRY(enqueue_stage_b(p, F, sb, &lb));
+            GOFPID_CUDA_TRY(cudaEventRecord(F.ev_blobs, sb));
         } else {
             GOFPID_CUDA_TRY(cudaEventRecord(F.ev_blobs, s));
         }
@@ -713,7 +729,7 @@ GOFPID_API int gofpid_pipeline_process_host(gofpid_pipeline *p, const uint8_t *h
 GOFPID_API int gofpid_pipeline_select(gofpid_pipeline *p, int age)
 {
     GOFPID_GUARD(p);
-    if (age < 0 || age >= DEPTH) { set_error("age must be 0 (newest frame) or 1 (the one before)"); return GOFPID_ERR_INVALID; }
+    if (age < 0 || age >= DEPTH) { set_error("age must be in [0, %d): 0 is the newest frame", DEPTH); return GOFPID_ERR_INVALID; }
     if (p->frames - 1 - age < 0) { set_error("no such frame yet"); return GOFPID_ERR_INVALID; }
     p->selected = age;
     return GOFPID_OK;

@@ -151,11 +151,11 @@ class HotPath:
 
     def submit_pinned(self, ptr, pitch, stream_stride):
         """Asynchronous process_pinned(): enqueue the H2D copy and the step, return at once.
-        Up to two frames are in flight; collect results with select(1) + the getters."""
+        Up to three frames are in flight; collect results with select(age) + the getters."""
         nat.check(self._L.gofpid_pipeline_submit_host(self._h, ptr, pitch, stream_stride))
 
     def select(self, age=0):
-        """Result getters refer to the newest frame (age 0) or the one before it (age 1)."""
+        """Result getters refer to the newest frame (age 0) or the ones before it (age 1, 2)."""
         nat.check(self._L.gofpid_pipeline_select(self._h, age))
 
     def process_device(self, ptr, pitch, stream_stride, cuda_stream=0):

@@ -193,6 +193,44 @@ def test_blobs_match_reference_semantics(runs_cap, monkeypatch):
             hp.close()
 
 
+@pytest.mark.parametrize("no_cond", ["0", "1"])
+def test_graph_replay_switches_between_run_and_tiled_labelling(no_cond, monkeypatch):
+    """Frames alternate between a few blobs (run-based labelling) and dense noise (more runs than the
+    capacity -> tiled fallback) while the step is replayed as a CUDA graph: the fallback kernels sit
+    in a conditional node (no_cond=1: plain early-exit launches) that must fire exactly when needed."""
+    import cv2
+    monkeypatch.setenv("GOFPID_RUNS_CAP", "200")
+    monkeypatch.setenv("GOFPID_NO_COND", no_cond)
+    rs = np.random.RandomState(8)
+    H, W = 120, 200
+    hp = _hot((H, W), blur=None, detector="FD", morph=(), find_blobs=True, fd_threshold=0, area_min=4.0)
+    prev = np.zeros((H, W), np.uint8)
+    hp.process(prev)
+    for t in range(12):
+        if t % 3 == 2:
+            M = ((rs.rand(H, W) < 0.4) * 255).astype(np.uint8)      # thousands of runs
+        else:
+            M = np.zeros((H, W), np.uint8)
+            for _ in range(5):
+                x, y = rs.randint(0, W - 30), rs.randint(0, H - 30)
+                cv2.rectangle(M, (x, y), (x + rs.randint(5, 30), y + rs.randint(5, 30)), 255, -1)
+        # FD gives |frame - previous| > 0: feed frames whose difference is the wanted mask
+        frame = np.where(M > 0, 255 - prev, prev).astype(np.uint8)
+        hp.process(frame)
+        want_mask = np.where(frame != prev, 255, 0).astype(np.uint8)
+        prev = frame
+        assert np.array_equal(hp.mask(), want_mask)
+        want = oblobs.blobs_from_mask(want_mask, area_min=4.0)
+        got = hp.blobs()
+        assert len(got) == len(want), (t, len(got), len(want))
+        for g, w in zip(got, want):
+            assert np.array_equal(g["contour"], w["contour"])
+        want_labels = cport.ccl8(want_mask)
+        assert np.array_equal(hp.labels(), want_labels), t
+        assert hp.components() == cport.component_stats(want_labels), t
+    hp.close()
+
+
 def test_blob_capacity_overflow_is_reported():
     from pygofpid_b200._native import GofpidError
     H, W = 64, 64
