@@ -279,7 +279,7 @@ def main():
 
     # ---- timed: end to end through the host entry points (pinned frames in, blob lists out) ----
     # Every frame is copied host->device inside the timed region and its blob list is read back
-    # to the host; frames t+1 and t+2 are submitted before frame t's results are collected (three
+    # to the host; frames t+1 .. t+3 are submitted before frame t's results are collected (four
     # frames in flight, the library's pipelined host API: submit_host / select / blobs).
     e2e_frames = F * max(1, args.steps // 4)
     for i in range(4):  # untimed: first use of the host path allocates its staging buffers
@@ -289,7 +289,7 @@ def main():
     w0 = time.perf_counter()
     d2h = 0
     nblobs = 0
-    LAG = 2  # frames submitted ahead of the one whose results are collected (3 frames in flight)
+    LAG = 3  # frames submitted ahead of the one whose results are collected (4 frames in flight)
     for i in range(e2e_frames + LAG):
         if i < e2e_frames:
             t = (t_idx + i) % n_clip
@@ -358,7 +358,7 @@ def main():
                     "mpix_per_s": e2e_fps * mpix,
                     "blobs_per_frame": nblobs / max(e2e_frames * S, 1),
                     "api": "gofpid_pipeline_submit_host + gofpid_pipeline_select + gofpid_pipeline_blobs "
-                           "(pinned host frames in, blob lists with contours out, 3 frames in flight)"},
+                           "(pinned host frames in, blob lists with contours out, 4 frames in flight)"},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic_per_launch(kname),

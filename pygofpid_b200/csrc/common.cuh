@@ -85,6 +85,7 @@ struct FrameTick {
     uint64_t knn_draw_off[3];  // draws before each refreshed tier's fill, within one stream
     uint64_t knn_draws;        // draws one stream consumes this frame (all refreshed tiers)
     uint64_t knn_rng;          // RNG state after this frame's fills (all streams)
+    int32_t mog2_done;      // tiles of the running mog2_kernel launch that have finished
     // FD
     int32_t fd_valid; // a previous frame exists
     // where this step's frames are (set by the tick kernel, the only node of the captured
@@ -151,7 +152,20 @@ const void *tick_kernel_func();
 void tick_kernel_params(TickArgs &a, void **params); // params[10]
 int launch_blur_only(const DetectLaunch &L, ImageU8 dst);
 int launch_fd(const DetectLaunch &L, FdModel model, int thr);
-int launch_mog2(const DetectLaunch &L, Mog2Model model, const Mog2Params &mp);
+// MOG2 derives its per-frame scalars itself (no tick kernel): by-value kernel arguments kept by the
+// pipeline so that a captured step can be replayed with a new frame pointer
+struct Mog2Args {
+    BlurParams bp;
+    ImageU8 mask;
+    Mog2Model M;
+    Mog2Params P;
+    FrameTick *tick;
+    FrameSrc src;
+    int H, W;
+};
+int launch_mog2(const DetectLaunch &L, Mog2Model model, const Mog2Params &mp, FrameTick *tick);
+const void *mog2_kernel_func(int C);
+void mog2_kernel_params(Mog2Args &a, void **params); // params[8]
 int launch_knn(const DetectLaunch &L, KnnModel model, const KnnParams &kp,
                const uint64_t *d_jump_table);
 int detect_launches_per_step(int detector);
@@ -178,6 +192,7 @@ struct MorphPlan {
     int n_levels;                       // 0: byte path
     int levels[3];
     int bit_tile_h, bit_hw_l, bit_hw_r; // tile rows, halo words left / right (tile width = 256 px)
+    int bit_pad;                        // spare rows above / below the staged rows in shared memory
     size_t bit_smem_bytes;
 };
 // Declares the set of non-zero values the chain's input can hold (at most 3); selects the bit-plane

@@ -392,8 +392,9 @@ morph_chain_kernel(MorphPlan plan, ImageU8 src, ImageU8 dst, int H, int W)
 // grey-level result is rebuilt from the planes on the way out.  A CTA owns 256 x tile_h pixels,
 // stages tile + accumulated halo (whole halo WORDS left and right) as bits, and also emits the
 // foreground bit image the blob stage works on.
-constexpr int MB_THREADS = 256;
+constexpr int MB_THREADS = 512;
 constexpr int MB_TWW = 8; // tile width in 32-pixel words
+constexpr int MB_R_PAD = 2; // spare rows for the last, partial block of output rows (>= MB_R - 1)
 
 void morph_plan_set_levels(MorphPlan *plan, const int *levels, int n_levels)
 {
@@ -412,7 +413,14 @@ void morph_plan_set_levels(MorphPlan *plan, const int *levels, int n_levels)
     plan->bit_tile_h = hmax > 8 ? 64 : 32;
     const size_t nw = plan->bit_hw_l + MB_TWW + plan->bit_hw_r;
     const size_t rows = plan->bit_tile_h + plan->halo_t + plan->halo_b;
-    plan->bit_smem_bytes = 2 * (size_t)n_levels * rows * nw * sizeof(uint32_t);
+    int pad = 0;
+    for (int i = 0; i < plan->n_ops; i++) {
+        const MorphOpDev &d = plan->ops[i];
+        pad = d.ay > pad ? d.ay : pad;
+        pad = d.kh - 1 - d.ay > pad ? d.kh - 1 - d.ay : pad;
+    }
+    plan->bit_pad = pad + MB_R_PAD;
+    plan->bit_smem_bytes = 2 * (size_t)n_levels * (rows + 2 * plan->bit_pad) * (nw + 2) * sizeof(uint32_t);
     if (plan->bit_smem_bytes > 160 * 1024) return; // enormous halo: stay on the byte path
     plan->n_levels = n_levels;
 }
@@ -475,92 +483,85 @@ __device__ __forceinline__ uint32_t row_window_k(uint32_t a, uint32_t b, uint32_
     return acc;
 }
 
-constexpr int MB_R = 4; // output rows per work item (a thread owns MB_R rows of one word column)
+constexpr int MB_R = 2;    // output rows per work item (a thread owns MB_R rows of one word column)
+constexpr int MB_MAXI = 4; // work items per thread decoded up front
 
-// One step on all planes: A -> B.  A work item is (plane, word column, block of MB_R rows); every
-// row of the buffer is computed (rows / bits whose support leaves the buffer come out wrong, but
-// by construction they lie in the part of the halo that later steps no longer read).
+// Shared-memory images are padded: one spare word left and right of every row and `pad` spare
+// rows above and below, so the windows are read without clamping.  Whatever the spare cells
+// hold only reaches bits whose support left the staged region, and those lie in the part of
+// the halo that later steps no longer read.
+struct BitItem {
+    int base;      // offset of (row r0, word w) in a padded plane, plus the plane offset
+    int r0, w;
+    uint32_t inm;  // in-image bits of word column w
+};
+
+// One step for one work item: output rows r0 .. r0+MB_R-1 of word column w.
 template <bool DIL, int K>
-__device__ __forceinline__ void run_op_bits(const MorphOpDev &op, const MorphRun *__restrict__ runs,
-                                            const uint32_t *A, uint32_t *B, int nl, const BitGeom &G,
-                                            uint32_t ident_next)
+__device__ __forceinline__ void op_item(const MorphOpDev &op, const MorphRun *__restrict__ runs,
+                                        const uint32_t *A, uint32_t *B, const BitItem &it, const BitGeom &G,
+                                        int NWP, uint32_t ident_next)
 {
-    const int NW = G.NW;
     const uint32_t ident = DIL ? 0u : 0xffffffffu;
-    const int nrb = (G.rows + MB_R - 1) / MB_R;
-    const int nitems = nl * NW * nrb;
-    for (int item = threadIdx.x; item < nitems; item += MB_THREADS) {
-        const int w = item % NW, t = item / NW;
-        const int rb = t % nrb, l = t / nrb;
-        const uint32_t *Ap = A + (size_t)l * G.plane;
-        uint32_t *Bp = B + (size_t)l * G.plane;
-        const int r0 = rb * MB_R;
-        uint32_t acc[MB_R];
+    const uint32_t *Ap = A + it.base;
+    uint32_t acc[MB_R];
 #pragma unroll
-        for (int q = 0; q < MB_R; q++) acc[q] = ident;
-        auto load3 = [&](int rr, uint32_t &a, uint32_t &b, uint32_t &c) {
-            const uint32_t *row = Ap + (size_t)min(max(rr, 0), G.rows - 1) * NW;
-            a = w > 0 ? row[w - 1] : ident; b = row[w]; c = w + 1 < NW ? row[w + 1] : ident;
-        };
-        if (K > 0) {
-            // K x K rectangle: K + MB_R - 1 row windows, each output row is the AND / OR of K of them
-            uint32_t h[MB_R + (K > 0 ? K : 1) - 1];
+    for (int q = 0; q < MB_R; q++) acc[q] = ident;
+    if (K > 0) {
+        // K x K rectangle: K + MB_R - 1 row windows, each output row is the AND / OR of K of them
+        constexpr int KK = K > 0 ? K : 1;
+        uint32_t h[MB_R + KK - 1];
 #pragma unroll
-            for (int i = 0; i < MB_R + K - 1; i++) {
-                uint32_t a, b, c;
-                load3(r0 - K / 2 + i, a, b, c);
-                h[i] = row_window_k<DIL, (K > 0 ? K : 1)>(a, b, c);
-            }
+        for (int i = 0; i < MB_R + KK - 1; i++) {
+            const uint32_t *row = Ap + (i - KK / 2) * NWP;
+            h[i] = row_window_k<DIL, KK>(row[-1], row[0], row[1]);
+        }
+#pragma unroll
+        for (int q = 0; q < MB_R; q++)
+#pragma unroll
+            for (int k = 0; k < KK; k++) acc[q] = DIL ? (acc[q] | h[q + k]) : (acc[q] & h[q + k]);
+    } else if (op.is_rect) {
+        const int top = op.ay, bot = op.kh - 1 - op.ay;
+        for (int rr = -top; rr < MB_R + bot; rr++) {
+            const uint32_t *row = Ap + rr * NWP;
+            const uint32_t hv = run_window<DIL>(row[-1], row[0], row[1], -op.ax, op.kw);
 #pragma unroll
             for (int q = 0; q < MB_R; q++)
-#pragma unroll
-                for (int k = 0; k < K; k++) acc[q] = DIL ? (acc[q] | h[q + k]) : (acc[q] & h[q + k]);
-        } else if (op.is_rect) {
-            const int top = op.ay, bot = op.kh - 1 - op.ay;
-            for (int rr = r0 - top; rr < r0 + MB_R + bot; rr++) {
-                uint32_t a, b, c;
-                load3(rr, a, b, c);
-                const uint32_t hv = run_window<DIL>(a, b, c, -op.ax, op.kw);
-#pragma unroll
-                for (int q = 0; q < MB_R; q++)
-                    if (rr >= r0 + q - top && rr <= r0 + q + bot) acc[q] = DIL ? (acc[q] | hv) : (acc[q] & hv);
-            }
-        } else {
-            for (int qi = op.run_begin; qi < op.run_end; qi++) {
-                const MorphRun run = runs[qi];
-#pragma unroll
-                for (int q = 0; q < MB_R; q++) {
-                    uint32_t a, b, c;
-                    load3(r0 + q + run.dy, a, b, c);
-                    const uint32_t v = run_window<DIL>(a, b, c, run.dx, run.len);
-                    acc[q] = DIL ? (acc[q] | v) : (acc[q] & v);
-                }
-            }
+                if (rr >= q - top && rr <= q + bot) acc[q] = DIL ? (acc[q] | hv) : (acc[q] & hv);
         }
-        // cells outside the image take the identity of the NEXT step (OpenCV ignores them)
-        const uint32_t inm = in_image_bits(G, w);
+    } else {
+        for (int qi = op.run_begin; qi < op.run_end; qi++) {
+            const MorphRun run = runs[qi];
 #pragma unroll
-        for (int q = 0; q < MB_R; q++) {
-            const int r = r0 + q;
-            if (r >= G.rows) break;
-            const int gy = G.gy0 + r;
-            const uint32_t m = (gy >= 0 && gy < G.H) ? inm : 0u;
-            Bp[(size_t)r * NW + w] = (acc[q] & m) | (ident_next & ~m);
+            for (int q = 0; q < MB_R; q++) {
+                const uint32_t *row = Ap + (q + run.dy) * NWP;
+                const uint32_t v = run_window<DIL>(row[-1], row[0], row[1], run.dx, run.len);
+                acc[q] = DIL ? (acc[q] | v) : (acc[q] & v);
+            }
         }
     }
-    __syncthreads();
+    // cells outside the image take the identity of the NEXT step (OpenCV ignores them)
+    uint32_t *Bp = B + it.base;
+#pragma unroll
+    for (int q = 0; q < MB_R; q++) {
+        const int r = it.r0 + q;
+        if (r >= G.rows) break;
+        const int gy = G.gy0 + r;
+        const uint32_t m = (gy >= 0 && gy < G.H) ? it.inm : 0u;
+        Bp[q * NWP] = (acc[q] & m) | (ident_next & ~m);
+    }
 }
 
 template <bool DIL>
-__device__ __forceinline__ void run_op_bits_dispatch(const MorphOpDev &op, const MorphRun *__restrict__ runs,
-                                                     const uint32_t *A, uint32_t *B, int nl,
-                                                     const BitGeom &G, uint32_t ident_next)
+__device__ __forceinline__ void op_item_dispatch(const MorphOpDev &op, const MorphRun *__restrict__ runs,
+                                                 const uint32_t *A, uint32_t *B, const BitItem &it,
+                                                 const BitGeom &G, int NWP, uint32_t ident_next)
 {
     const bool sq = op.is_rect && op.kw == op.kh && (op.kw & 1);
-    if (sq && op.kw == 5) run_op_bits<DIL, 5>(op, runs, A, B, nl, G, ident_next);
-    else if (sq && op.kw == 3) run_op_bits<DIL, 3>(op, runs, A, B, nl, G, ident_next);
-    else if (sq && op.kw == 7) run_op_bits<DIL, 7>(op, runs, A, B, nl, G, ident_next);
-    else run_op_bits<DIL, 0>(op, runs, A, B, nl, G, ident_next);
+    if (sq && op.kw == 5) op_item<DIL, 5>(op, runs, A, B, it, G, NWP, ident_next);
+    else if (sq && op.kw == 3) op_item<DIL, 3>(op, runs, A, B, it, G, NWP, ident_next);
+    else if (sq && op.kw == 7) op_item<DIL, 7>(op, runs, A, B, it, G, NWP, ident_next);
+    else op_item<DIL, 0>(op, runs, A, B, it, G, NWP, ident_next);
 }
 
 __global__ void __launch_bounds__(MB_THREADS)
@@ -573,7 +574,9 @@ morph_bits_kernel(MorphPlan plan, ImageU8 src, ImageU8 dst, uint32_t *bitimg, in
     BitGeom G;
     G.NW = plan.bit_hw_l + MB_TWW + plan.bit_hw_r;
     G.rows = plan.bit_tile_h + plan.halo_t + plan.halo_b;
-    G.plane = G.rows * G.NW;
+    const int NWP = G.NW + 2, pad = plan.bit_pad;
+    G.plane = (G.rows + 2 * pad) * NWP;                   // words per padded plane
+    const int org = pad * NWP + 1;                        // offset of cell (0, 0) inside a plane
     const int x0 = blockIdx.x * (MB_TWW * 32), y0 = blockIdx.y * plan.bit_tile_h;
     G.gx0 = x0 - 32 * plan.bit_hw_l; G.gy0 = y0 - plan.halo_t; G.H = H; G.W = W;
     uint32_t *A = reinterpret_cast<uint32_t *>(smem);
@@ -589,7 +592,8 @@ morph_bits_kernel(MorphPlan plan, ImageU8 src, ImageU8 dst, uint32_t *bitimg, in
 
     // ---- stage tile + halo as threshold bits; out-of-image cells get the first step's identity
     bool any = false;
-    for (int i = tid; i < G.plane; i += MB_THREADS) {
+    const int ncell = G.rows * G.NW;
+    for (int i = tid; i < ncell; i += MB_THREADS) {
         const int r = i / G.NW, w = i - r * G.NW;
         const int gy = G.gy0 + r, gx = G.gx0 + 32 * w;
         uint32_t bits[3] = {0u, 0u, 0u};
@@ -614,21 +618,59 @@ morph_bits_kernel(MorphPlan plan, ImageU8 src, ImageU8 dst, uint32_t *bitimg, in
                                     (ge4(v[3], lv4[l]) << 12)) << (16 * h);
             }
         }
+        const int cell = org + r * NWP + w;
 #pragma unroll
         for (int l = 0; l < 3; l++)
-            if (l < nl) A[(size_t)l * G.plane + i] = (bits[l] & m) | (ident0 & ~m);
+            if (l < nl) A[(size_t)l * G.plane + cell] = (bits[l] & m) | (ident0 & ~m);
         any |= (bits[0] & m) != 0u;
     }
     const bool nonempty = __syncthreads_or(any) || !plan.anchored;
 
     const int tile_h = plan.bit_tile_h;
     if (nonempty) {
+        // the thread's work items, decoded once: (plane, word column, block of MB_R rows)
+        const int nrb = (G.rows + MB_R - 1) / MB_R;
+        const int nitems = nl * G.NW * nrb;
+        BitItem items[MB_MAXI];
+        int n_mine = 0;
+#pragma unroll
+        for (int q = 0; q < MB_MAXI; q++) {
+            const int item = tid + q * MB_THREADS;
+            items[q].base = 0; items[q].r0 = 0; items[q].w = 0; items[q].inm = 0u;
+            if (item < nitems) {
+                const int w = item % G.NW, t = item / G.NW;
+                const int rb = t % nrb, l = t / nrb;
+                items[q].w = w; items[q].r0 = rb * MB_R;
+                items[q].base = l * G.plane + org + rb * MB_R * NWP + w;
+                items[q].inm = in_image_bits(G, w);
+                n_mine = q + 1;
+            }
+        }
+        const bool small = nitems <= MB_MAXI * MB_THREADS;
         for (int k = 0; k < plan.n_ops; k++) {
             const MorphOpDev &op = plan.ops[k];
             const uint32_t ident_next =
                 (k + 1 < plan.n_ops && plan.ops[k + 1].op == GOFPID_MORPH_ERODE) ? 0xffffffffu : 0u;
-            if (op.op == GOFPID_MORPH_DILATE) run_op_bits_dispatch<true>(op, plan.d_runs, A, B, nl, G, ident_next);
-            else run_op_bits_dispatch<false>(op, plan.d_runs, A, B, nl, G, ident_next);
+            const bool dil = op.op == GOFPID_MORPH_DILATE;
+            if (small) {
+#pragma unroll
+                for (int q = 0; q < MB_MAXI; q++)
+                    if (q < n_mine) {
+                        if (dil) op_item_dispatch<true>(op, plan.d_runs, A, B, items[q], G, NWP, ident_next);
+                        else op_item_dispatch<false>(op, plan.d_runs, A, B, items[q], G, NWP, ident_next);
+                    }
+            } else {
+                for (int item = tid; item < nitems; item += MB_THREADS) {
+                    BitItem it;
+                    const int w = item % G.NW, t = item / G.NW;
+                    const int rb = t % nrb, l = t / nrb;
+                    it.w = w; it.r0 = rb * MB_R; it.base = l * G.plane + org + rb * MB_R * NWP + w;
+                    it.inm = in_image_bits(G, w);
+                    if (dil) op_item_dispatch<true>(op, plan.d_runs, A, B, it, G, NWP, ident_next);
+                    else op_item_dispatch<false>(op, plan.d_runs, A, B, it, G, NWP, ident_next);
+                }
+            }
+            __syncthreads();
             uint32_t *t = A; A = B; B = t;
         }
     }
@@ -641,7 +683,7 @@ morph_bits_kernel(MorphPlan plan, ImageU8 src, ImageU8 dst, uint32_t *bitimg, in
         const int w = hw >> 1, h = hw & 1;
         const int gy = y0 + r, gx = x0 + 32 * w + 16 * h;
         if (gy >= H || gx >= W) continue;
-        const size_t si = (size_t)(r + plan.halo_t) * G.NW + plan.bit_hw_l + w;
+        const size_t si = (size_t)org + (size_t)(r + plan.halo_t) * NWP + plan.bit_hw_l + w;
         uint32_t p[3] = {0u, 0u, 0u};
         if (nonempty) {
 #pragma unroll

@@ -36,10 +36,12 @@ using namespace gofpid;
 // sequential; stage B only needs the finished mask of its own frame and occupies a handful of
 // SMs (one CTA per stream or per blob), so consecutive frames of ONE camera stream overlap and
 // the frame rate is set by stage A alone.
-constexpr int DEPTH = 3;
+constexpr int MAX_DEPTH = 6;
+constexpr int DEFAULT_DEPTH = 4; // GOFPID_DEPTH overrides (1 .. MAX_DEPTH)
 
 struct FrameSlot {
     uint8_t *d_final = nullptr;   // final mask of the frame in this slot
+    uint8_t *d_mask_det = nullptr; // detector output of the frame when a morphology chain follows
     BlobBuffers blobs = {};
     cudaEvent_t ev_mask = nullptr, ev_blobs = nullptr; // stage A / stage B of this slot finished
     gofpid_frame_info *h_info = nullptr;               // pinned host copies of the results
@@ -52,7 +54,9 @@ struct FrameSlot {
     // stage graphs of this slot (buffers are baked into the kernel arguments)
     cudaGraph_t graph_a = nullptr, graph_b = nullptr;
     cudaGraphExec_t exec_a = nullptr, exec_b = nullptr;
-    cudaGraphNode_t tick_node = nullptr;
+    cudaGraphNode_t tick_node = nullptr;   // the node of stage A that takes the frame pointer (tick or MOG2 kernel)
+    cudaKernelNodeParams src_node_params = {}; // its launch geometry, as captured
+    Mog2Args mog2_args;                    // by-value MOG2 kernel arguments of this slot
     cudaGraphConditionalHandle cond_b = 0; // raised by runs_ccl_kernel: run the tiled labelling fallback
 };
 
@@ -61,7 +65,9 @@ struct gofpid_pipeline {
     std::vector<std::vector<uint8_t>> se_copies;
     int H = 0, W = 0, C = 0, n_streams = 0, device = 0;
     cudaStream_t stream = nullptr;   // own stage-A stream (host entry points)
-    cudaStream_t stream_b[DEPTH] = {}; // stage B, one per frame slot
+    cudaStream_t stream_b[MAX_DEPTH] = {}; // stage B, one per frame slot
+    int depth = DEFAULT_DEPTH;            // frame slots in use
+    int prefix_kept = 0, prefix_points = 0; // blob records / contour points copied to the host with every step
     cudaStream_t stream_c = nullptr; // result fetches
     cudaStream_t stream_h = nullptr; // host->device frame copies
     BlurParams blur;
@@ -70,7 +76,6 @@ struct gofpid_pipeline {
     int fd_thr = 0;
 
     FrameTick *d_tick = nullptr;
-    uint8_t *d_mask_det = nullptr; // detector output when a morphology chain follows
     size_t mask_pitch = 0, mask_stream = 0;
 
     Mog2Model mog2 = {};
@@ -81,7 +86,7 @@ struct gofpid_pipeline {
     uint64_t *d_pow2tab = nullptr;
 
     MorphPlan morph = {};
-    FrameSlot slots[DEPTH];
+    FrameSlot slots[MAX_DEPTH];
     long frames = 0;  // frames submitted so far
     int selected = 0; // age of the frame the result getters refer to (0 newest, 1 previous)
 
@@ -157,7 +162,7 @@ FrameSlot *selected_slot(gofpid_pipeline *p)
 {
     const long idx = p->frames - 1 - p->selected;
     if (idx < 0) return nullptr;
-    FrameSlot *S = &p->slots[idx % DEPTH];
+    FrameSlot *S = &p->slots[idx % p->depth];
     return S->used ? S : nullptr;
 }
 
@@ -186,7 +191,6 @@ int reset_state(gofpid_pipeline *p)
 void free_all(gofpid_pipeline *p)
 {
     cudaFree(p->d_tick);
-    cudaFree(p->d_mask_det);
     cudaFree(p->mog2.planes); cudaFree(p->mog2.nmodes); cudaFree(p->mog2.tile_nmax);
     cudaFree(p->knn.samples); cudaFree(p->knn.nxt); cudaFree(p->knn.idx); cudaFree(p->knn.fresh);
     cudaFree(p->fd.prev);
@@ -194,6 +198,7 @@ void free_all(gofpid_pipeline *p)
     morph_plan_destroy(&p->morph);
     for (auto &S : p->slots) {
         cudaFree(S.d_final);
+        cudaFree(S.d_mask_det);
         run_list_free(&S.blobs.runs);
         cudaFree(S.blobs.labels); cudaFree(S.blobs.slot); cudaFree(S.blobs.comp); cudaFree(S.blobs.bitimg);
         cudaFree(S.blobs.info); cudaFree(S.blobs.kept); cudaFree(S.blobs.points);
@@ -223,14 +228,24 @@ int build(gofpid_pipeline *p)
     const int H = p->H, W = p->W, C = p->C, S = p->n_streams;
     for (cudaStream_t *s : {&p->stream, &p->stream_c, &p->stream_h})
         GOFPID_CUDA_TRY(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking));
-    for (cudaStream_t &s : p->stream_b) GOFPID_CUDA_TRY(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    {
+        const char *e = getenv("GOFPID_DEPTH");
+        if (e && atoi(e) >= 1 && atoi(e) <= MAX_DEPTH) p->depth = atoi(e);
+        // stage B runs at a higher priority than stage A: its few CTAs take the SMs they need as soon
+        // as the detector's CTAs drain instead of queueing behind the whole grid
+        int lo = 0, hi = 0;
+        GOFPID_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        const char *pe = getenv("GOFPID_B_PRIO");
+        const int prio = (pe && pe[0] == '0') ? lo : hi;
+        for (int i = 0; i < p->depth; i++)
+            GOFPID_CUDA_TRY(cudaStreamCreateWithPriority(&p->stream_b[i], cudaStreamNonBlocking, prio));
+    }
     for (auto &e : p->ev) GOFPID_CUDA_TRY(cudaEventCreate(&e));
     GOFPID_TRY(make_blur_params(cfg.blur_kind, cfg.blur_kw, cfg.blur_kh, cfg.blur_sigma, &p->blur));
 
     GOFPID_TRY(alloc_zero((void **)&p->d_tick, sizeof(FrameTick)));
     p->mask_pitch = round_up((size_t)W, 128);
     p->mask_stream = p->mask_pitch * H;
-    if (cfg.n_morph > 0) GOFPID_TRY(alloc_zero((void **)&p->d_mask_det, p->mask_stream * S));
 
     const int PW = (int)round_up((size_t)W, 32);
     const size_t pe = (size_t)PW * H;
@@ -320,8 +335,10 @@ int build(gofpid_pipeline *p)
         if (W > 8191 || H > 32767) { set_error("frames beyond 8191 x 32767 are not supported by the border tracer"); return GOFPID_ERR_UNSUPPORTED; }
         if (round_up((size_t)W, 4) * H >= (size_t)0x7fffffff) { set_error("frame too large for int32 labels"); return GOFPID_ERR_UNSUPPORTED; }
     }
-    for (auto &F : p->slots) {
+    for (int si = 0; si < p->depth; si++) {
+        FrameSlot &F = p->slots[si];
         GOFPID_TRY(alloc_zero((void **)&F.d_final, p->mask_stream * S));
+        if (cfg.n_morph > 0) GOFPID_TRY(alloc_zero((void **)&F.d_mask_det, p->mask_stream * S));
         GOFPID_CUDA_TRY(cudaEventCreateWithFlags(&F.ev_mask, cudaEventDisableTiming));
         GOFPID_CUDA_TRY(cudaEventCreateWithFlags(&F.ev_blobs, cudaEventDisableTiming));
         GOFPID_CUDA_TRY(cudaEventCreateWithFlags(&F.ev_h2d, cudaEventDisableTiming));
@@ -330,6 +347,8 @@ int build(gofpid_pipeline *p)
         if (!cfg.find_blobs) continue;
         BlobBuffers &B = F.blobs;
         B.max_blobs = cfg.max_blobs; B.max_kept = cfg.max_kept; B.max_points = cfg.max_points;
+        p->prefix_kept = std::min(cfg.max_kept, 256);
+        p->prefix_points = std::min(cfg.max_points, std::max(4096, 8 * (H + W)));
         B.area_min = cfg.blob_area_min;
         B.labels_pitch = round_up((size_t)W, 4);
         B.labels_stream = B.labels_pitch * H;
@@ -349,48 +368,71 @@ int build(gofpid_pipeline *p)
     return reset_state(p);
 }
 
-// ---- stage A: tick, blur + detect, morphology -> the slot's final mask -------------------------
+// ---- stage A: tick, blur + detect -> the slot's detector mask -------------------------------------
+// (the only part of a step that is sequential in time: the background model)
 int enqueue_stage_a(gofpid_pipeline *p, FrameSlot &F, const FrameSrc &src, cudaStream_t s, bool prof,
                     int *n_launches)
 {
     int launches = 0;
     if (prof) GOFPID_CUDA_TRY(cudaEventRecord(p->ev[0], s));
-    p->tick_args.src = src;
-    GOFPID_TRY(launch_tick(p->tick_args, s));
+    const bool mog2 = p->cfg.detector == GOFPID_DETECT_MOG2;
+    if (!mog2) { // (MOG2 derives its per-frame scalars inside the fused kernel)
+        p->tick_args.src = src;
+        GOFPID_TRY(launch_tick(p->tick_args, s));
+    }
     if (prof) GOFPID_CUDA_TRY(cudaEventRecord(p->ev[4], s));
     DetectLaunch L;
     L.H = p->H; L.W = p->W; L.C = p->C; L.n_streams = p->n_streams;
     L.src = src;
     L.blur = p->blur;
-    L.mask = ImageU8{p->cfg.n_morph > 0 ? p->d_mask_det : F.d_final, p->mask_pitch, p->mask_stream};
+    L.mask = ImageU8{p->cfg.n_morph > 0 ? F.d_mask_det : F.d_final, p->mask_pitch, p->mask_stream};
     L.tick = p->d_tick;
     L.stream = s;
-    if (p->cfg.detector == GOFPID_DETECT_MOG2) GOFPID_TRY(launch_mog2(L, p->mog2, p->mog2p));
+    if (mog2) {
+        GOFPID_TRY(launch_mog2(L, p->mog2, p->mog2p, p->d_tick));
+        F.mog2_args = Mog2Args{L.blur, L.mask, p->mog2, p->mog2p, p->d_tick, src, p->H, p->W};
+    }
     else if (p->cfg.detector == GOFPID_DETECT_KNN) GOFPID_TRY(launch_knn(L, p->knn, p->knnp, p->d_pow2tab));
     else GOFPID_TRY(launch_fd(L, p->fd, p->fd_thr));
     launches += detect_launches_per_step(p->cfg.detector);
     if (prof) GOFPID_CUDA_TRY(cudaEventRecord(p->ev[1], s));
-    if (p->cfg.n_morph > 0) {
-        const bool bits = p->morph.n_levels > 0 && p->cfg.find_blobs;
-        GOFPID_TRY(launch_morph(p->morph, L.mask, ImageU8{F.d_final, p->mask_pitch, p->mask_stream},
-                                p->H, p->W, p->n_streams, s, bits ? F.blobs.bitimg : nullptr,
-                                F.blobs.bit_pitch, F.blobs.bit_stream));
-        launches += 1;
-    }
-    if (prof) GOFPID_CUDA_TRY(cudaEventRecord(p->ev[2], s));
     if (n_launches) *n_launches = launches;
     return GOFPID_OK;
 }
 
-// ---- stage B: labelling, statistics, border tracing on the slot's final mask ---------------------
-int enqueue_stage_b(gofpid_pipeline *p, FrameSlot &F, cudaStream_t s, int *n_launches,
+// ---- stage B: morphology -> the slot's final mask, then run extraction, labelling, border tracing ---
+// (depends only on its own frame's detector mask, so the stage Bs of consecutive frames overlap
+// each other and the next frames' stage A)
+int enqueue_stage_b(gofpid_pipeline *p, FrameSlot &F, cudaStream_t s, bool prof, int *n_launches,
                     const cudaGraphConditionalHandle *cond = nullptr)
 {
-    int nb = 0;
+    int nb = 0, nm = 0;
+    if (p->cfg.n_morph > 0) {
+        const bool bits = p->morph.n_levels > 0 && p->cfg.find_blobs;
+        GOFPID_TRY(launch_morph(p->morph, ImageU8{F.d_mask_det, p->mask_pitch, p->mask_stream},
+                                ImageU8{F.d_final, p->mask_pitch, p->mask_stream},
+                                p->H, p->W, p->n_streams, s, bits ? F.blobs.bitimg : nullptr,
+                                F.blobs.bit_pitch, F.blobs.bit_stream));
+        nm = 1;
+    }
+    if (prof) GOFPID_CUDA_TRY(cudaEventRecord(p->ev[2], s));
     if (p->cfg.find_blobs)
         GOFPID_TRY(launch_blobs(F.blobs, ImageU8{F.d_final, p->mask_pitch, p->mask_stream}, p->H, p->W,
                                 p->n_streams, nullptr, s, &nb, p->cfg.n_morph > 0 && p->morph.n_levels > 0, cond));
-    if (n_launches) *n_launches = nb;
+    if (p->cfg.find_blobs) {
+        // results travel to pinned host memory as part of the step (no host round trip to learn the
+        // sizes first): headers, and a prefix of the blob records / contour points that holds a
+        // normal frame entirely; fetch_results() copies the rest of an unusually busy frame
+        const BlobBuffers &B = F.blobs;
+        const int S = p->n_streams;
+        GOFPID_CUDA_TRY(cudaMemcpyAsync(F.h_info, B.info, sizeof(gofpid_frame_info) * S, cudaMemcpyDeviceToHost, s));
+        GOFPID_CUDA_TRY(cudaMemcpy2DAsync(F.h_kept, sizeof(gofpid_blob) * B.max_kept, B.kept, sizeof(gofpid_blob) * B.max_kept,
+                                          sizeof(gofpid_blob) * p->prefix_kept, S, cudaMemcpyDeviceToHost, s));
+        GOFPID_CUDA_TRY(cudaMemcpy2DAsync(F.h_points, sizeof(int32_t) * 2 * B.max_points, B.points,
+                                          sizeof(int32_t) * 2 * B.max_points, sizeof(int32_t) * 2 * p->prefix_points, S,
+                                          cudaMemcpyDeviceToHost, s));
+    }
+    if (n_launches) *n_launches = nb + nm;
     return GOFPID_OK;
 }
 
@@ -414,20 +456,21 @@ int build_graphs(gofpid_pipeline *p, FrameSlot &F, const FrameSrc &src)
         if (t != cudaGraphNodeTypeKernel) continue;
         cudaKernelNodeParams kp;
         GOFPID_CUDA_TRY(cudaGraphKernelNodeGetParams(nodes[i], &kp));
-        if (kp.func == tick_kernel_func()) { F.tick_node = nodes[i]; break; }
+        const void *want = p->cfg.detector == GOFPID_DETECT_MOG2 ? mog2_kernel_func(p->C) : tick_kernel_func();
+        if (kp.func == want) { F.tick_node = nodes[i]; F.src_node_params = kp; break; }
     }
-    if (!F.tick_node) { set_error("graph capture: tick node not found"); return GOFPID_ERR_CUDA; }
+    if (!F.tick_node) { set_error("graph capture: frame-source node not found"); return GOFPID_ERR_CUDA; }
     GOFPID_CUDA_TRY(cudaGraphInstantiate(&F.exec_a, F.graph_a, 0));
-    if (p->cfg.find_blobs) {
+    if (p->cfg.find_blobs || p->cfg.n_morph > 0) {
         const char *nc = getenv("GOFPID_NO_COND");
-        const bool use_cond = !(nc && nc[0] == '1');
+        const bool use_cond = p->cfg.find_blobs && !(nc && nc[0] == '1');
         GOFPID_CUDA_TRY(cudaGraphCreate(&F.graph_b, 0));
         if (use_cond)
             GOFPID_CUDA_TRY(cudaGraphConditionalHandleCreate(&F.cond_b, F.graph_b, 0, cudaGraphCondAssignDefault));
         cudaStream_t sb = p->stream_b[&F - p->slots];
         GOFPID_CUDA_TRY(cudaStreamBeginCaptureToGraph(sb, F.graph_b, nullptr, nullptr, 0,
                                                       cudaStreamCaptureModeThreadLocal));
-        rc = enqueue_stage_b(p, F, sb, &lb, use_cond ? &F.cond_b : nullptr);
+        rc = enqueue_stage_b(p, F, sb, false, &lb, use_cond ? &F.cond_b : nullptr);
         cudaGraph_t captured = nullptr;
         e = cudaStreamEndCapture(sb, &captured);
         if (rc != GOFPID_OK) return rc;
@@ -443,28 +486,31 @@ int run_step(gofpid_pipeline *p, const uint8_t *d_frames, size_t pitch, size_t s
              cudaStream_t s)
 {
     const FrameSrc src{d_frames, pitch, stream_stride};
-    FrameSlot &F = p->slots[p->frames % DEPTH];
+    FrameSlot &F = p->slots[p->frames % p->depth];
     int la = 0, lb = 0;
     // the slot's previous frame (t - DEPTH) must be done with its mask before it is overwritten
     if (F.used) GOFPID_CUDA_TRY(cudaStreamWaitEvent(s, F.ev_blobs, 0));
     if (p->profiling) {
         // everything on one stream, with events between the stages
         GOFPID_TRY(enqueue_stage_a(p, F, src, s, true, &la));
-        GOFPID_TRY(enqueue_stage_b(p, F, s, &lb));
+        GOFPID_TRY(enqueue_stage_b(p, F, s, true, &lb));
         GOFPID_CUDA_TRY(cudaEventRecord(p->ev[3], s));
         GOFPID_CUDA_TRY(cudaEventRecord(F.ev_mask, s));
         GOFPID_CUDA_TRY(cudaEventRecord(F.ev_blobs, s));
     } else {
         // (the first DEPTH steps run eagerly: they also perform the one-time function setup)
-        const bool graph = p->use_graph && p->frames >= DEPTH;
+        const bool graph = p->use_graph && p->frames >= p->depth;
         if (graph && !F.exec_a) GOFPID_TRY(build_graphs(p, F, src));
         if (graph) {
-            p->tick_args.src = src;
             void *params[10];
-            tick_kernel_params(p->tick_args, params);
-            cudaKernelNodeParams kp = {};
-            kp.func = const_cast<void *>(tick_kernel_func());
-            kp.gridDim = dim3(1); kp.blockDim = dim3(32); kp.sharedMemBytes = 0;
+            if (p->cfg.detector == GOFPID_DETECT_MOG2) {
+                F.mog2_args.src = src;
+                mog2_kernel_params(F.mog2_args, params);
+            } else {
+                p->tick_args.src = src;
+                tick_kernel_params(p->tick_args, params);
+            }
+            cudaKernelNodeParams kp = F.src_node_params; // launch geometry as captured, new arguments
             kp.kernelParams = params; kp.extra = nullptr;
             GOFPID_CUDA_TRY(cudaGraphExecKernelNodeSetParams(F.exec_a, F.tick_node, &kp));
             GOFPID_CUDA_TRY(cudaGraphLaunch(F.exec_a, s));
@@ -473,11 +519,11 @@ int run_step(gofpid_pipeline *p, const uint8_t *d_frames, size_t pitch, size_t s
             GOFPID_TRY(enqueue_stage_a(p, F, src, s, false, &la));
         }
         GOFPID_CUDA_TRY(cudaEventRecord(F.ev_mask, s));
-        if (p->cfg.find_blobs) {
+        if (p->cfg.find_blobs || p->cfg.n_morph > 0) {
             cudaStream_t sb = p->stream_b[&F - p->slots];
             GOFPID_CUDA_TRY(cudaStreamWaitEvent(sb, F.ev_mask, 0));
             if (graph) GOFPID_CUDA_TRY(cudaGraphLaunch(F.exec_b, sb));
-            else GOFPID_TRY(enqueue_stage_b(p, F, sb, &lb));
+            else GOFPID_TRY(enqueue_stage_b(p, F, sb, false, &lb));
             GOFPID_CUDA_TRY(cudaEventRecord(F.ev_blobs, sb));
         } else {
             GOFPID_CUDA_TRY(cudaEventRecord(F.ev_blobs, s));
@@ -505,22 +551,22 @@ int fetch_results(gofpid_pipeline *p, FrameSlot *F)
     }
     cudaStream_t s = p->stream_c;
     const BlobBuffers &B = F->blobs;
-    GOFPID_CUDA_TRY(cudaMemcpyAsync(F->h_info, B.info, sizeof(gofpid_frame_info) * S, cudaMemcpyDeviceToHost, s));
-    GOFPID_CUDA_TRY(cudaStreamSynchronize(s));
+    // headers and the usual amount of records / points arrived with the step (enqueue_stage_b)
     bool any = false;
     for (int z = 0; z < S; z++) {
         F->h_info[z].frame_index = F->frame_index;
         const int nk = std::min(F->h_info[z].n_kept, B.max_kept);
         const int np = std::min(F->h_info[z].n_points, B.max_points);
-        if (nk > 0) {
-            GOFPID_CUDA_TRY(cudaMemcpyAsync(F->h_kept + (size_t)z * B.max_kept, B.kept + (size_t)z * B.max_kept,
-                                            sizeof(gofpid_blob) * nk, cudaMemcpyDeviceToHost, s));
+        if (nk > p->prefix_kept) {
+            GOFPID_CUDA_TRY(cudaMemcpyAsync(F->h_kept + (size_t)z * B.max_kept + p->prefix_kept,
+                                            B.kept + (size_t)z * B.max_kept + p->prefix_kept,
+                                            sizeof(gofpid_blob) * (nk - p->prefix_kept), cudaMemcpyDeviceToHost, s));
             any = true;
         }
-        if (np > 0) {
-            GOFPID_CUDA_TRY(cudaMemcpyAsync(F->h_points + (size_t)z * B.max_points * 2,
-                                            B.points + (size_t)z * B.max_points * 2,
-                                            sizeof(int32_t) * 2 * np, cudaMemcpyDeviceToHost, s));
+        if (np > p->prefix_points) {
+            GOFPID_CUDA_TRY(cudaMemcpyAsync(F->h_points + ((size_t)z * B.max_points + p->prefix_points) * 2,
+                                            B.points + ((size_t)z * B.max_points + p->prefix_points) * 2,
+                                            sizeof(int32_t) * 2 * (np - p->prefix_points), cudaMemcpyDeviceToHost, s));
             any = true;
         }
     }
@@ -534,12 +580,14 @@ int submit_host(gofpid_pipeline *p, const uint8_t *h_frames, size_t pitch, size_
 {
     const size_t row = (size_t)p->W * p->C;
     if (pitch < row) { set_error("pitch %zu smaller than a row (%zu bytes)", pitch, row); return GOFPID_ERR_INVALID; }
-    FrameSlot &F = p->slots[p->frames % DEPTH];
+    FrameSlot &F = p->slots[p->frames % p->depth];
     if (!p->frames_pitch) {
         p->frames_pitch = round_up(row, 128);
         p->frames_stream = p->frames_pitch * p->H;
     }
-    if (!F.d_frames) GOFPID_CUDA_TRY(cudaMalloc(&F.d_frames, p->frames_stream * p->n_streams));
+    if (!F.d_frames)
+        for (int si = 0; si < p->depth; si++) // (all slots at once: no allocation inside a running pipeline)
+            if (!p->slots[si].d_frames) GOFPID_CUDA_TRY(cudaMalloc(&p->slots[si].d_frames, p->frames_stream * p->n_streams));
     cudaPointerAttributes attr;
     bool pinned = false;
     if (cudaPointerGetAttributes(&attr, h_frames) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
@@ -729,7 +777,7 @@ GOFPID_API int gofpid_pipeline_process_host(gofpid_pipeline *p, const uint8_t *h
 GOFPID_API int gofpid_pipeline_select(gofpid_pipeline *p, int age)
 {
     GOFPID_GUARD(p);
-    if (age < 0 || age >= DEPTH) { set_error("age must be in [0, %d): 0 is the newest frame", DEPTH); return GOFPID_ERR_INVALID; }
+    if (age < 0 || age >= p->depth) { set_error("age must be in [0, %d): 0 is the newest frame", p->depth); return GOFPID_ERR_INVALID; }
     if (p->frames - 1 - age < 0) { set_error("no such frame yet"); return GOFPID_ERR_INVALID; }
     p->selected = age;
     return GOFPID_OK;
@@ -801,7 +849,7 @@ GOFPID_API int gofpid_pipeline_mask(gofpid_pipeline *p, int stream_idx, uint8_t 
     if (!dst || dst_pitch < (size_t)p->W) { set_error("bad destination"); return GOFPID_ERR_INVALID; }
     FrameSlot *F = selected_slot(p);
     if (!F) { set_error("no frame has been processed yet"); return GOFPID_ERR_INVALID; }
-    GOFPID_CUDA_TRY(cudaEventSynchronize(F->ev_mask));
+    GOFPID_CUDA_TRY(cudaEventSynchronize(F->ev_blobs)); // (the final mask is written by stage B's first kernel)
     const uint8_t *src = F->d_final + (size_t)stream_idx * p->mask_stream;
     GOFPID_CUDA_TRY(cudaMemcpy2DAsync(dst, dst_pitch, src, p->mask_pitch, p->W, p->H,
                                       dst_is_device ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost,

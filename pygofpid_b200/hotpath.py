@@ -194,16 +194,24 @@ class HotPath:
 
     def raw_blobs(self, stream=0):
         """(records, points): structured blob records in the reference's order and one
-        (n_points, 2) int32 array of contour points."""
+        (n_points, 2) int32 array of contour points.
+
+        One library call into reusable buffers sized for a normal frame; a busier frame (the call
+        reports the sizes it needs) is fetched again into buffers of that size."""
         nb, npt = ct.c_int(0), ct.c_int(0)
-        nat.check(self._L.gofpid_pipeline_blobs(self._h, stream, None, 0, None, 0, ct.byref(nb),
-                                                ct.byref(npt)))
-        recs = (nat.Blob * max(nb.value, 1))()
-        pts = np.empty((max(npt.value, 1), 2), np.int32)
-        nat.check(self._L.gofpid_pipeline_blobs(self._h, stream, recs, nb.value,
-                                                pts.ctypes.data_as(ct.POINTER(ct.c_int32)), npt.value,
-                                                ct.byref(nb), ct.byref(npt)))
-        return recs[:nb.value], pts[:npt.value]
+        cap_b, cap_p = getattr(self, "_blob_cap", (64, 8192))
+        while True:
+            recs = (nat.Blob * cap_b)()
+            pts = np.empty((cap_p, 2), np.int32)
+            rc = self._L.gofpid_pipeline_blobs(self._h, stream, recs, cap_b,
+                                               pts.ctypes.data_as(ct.POINTER(ct.c_int32)), cap_p,
+                                               ct.byref(nb), ct.byref(npt))
+            if rc == nat.ERR_INVALID and (nb.value > cap_b or npt.value > cap_p):
+                cap_b, cap_p = max(cap_b, 2 * nb.value), max(cap_p, 2 * npt.value)
+                self._blob_cap = (cap_b, cap_p)
+                continue
+            nat.check(rc)
+            return recs[:nb.value], pts[:npt.value]
 
     def blobs(self, stream=0, anchor="bottom"):
         """self.blobs_ of the reference (pipeline.py:555-588): list of dicts with keys

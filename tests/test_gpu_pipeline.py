@@ -231,6 +231,30 @@ def test_graph_replay_switches_between_run_and_tiled_labelling(no_cond, monkeypa
     hp.close()
 
 
+def test_busy_frame_beyond_the_prefetched_result_prefix():
+    """More kept blobs (> 256) and contour points (> 4096) than travel to the host with the step:
+    the remainder is fetched on demand and the blob list is still complete and in order."""
+    H, W = 200, 300
+    M = np.zeros((H, W), np.uint8)
+    for y in range(2, H - 6, 8):
+        for x in range(2, W - 6, 8):
+            M[y:y + 6, x:x + 6] = 255          # 24 x 37 = 888 squares of 20 contour points
+    hp = _hot((H, W), blur=None, detector="FD", morph=(), find_blobs=True, fd_threshold=0, area_min=4.0)
+    hp.process(np.zeros((H, W), np.uint8))
+    for _ in range(6):                          # eager steps and graph replays alike
+        hp.process(M)
+        hp.process(np.zeros((H, W), np.uint8))
+    hp.process(M)
+    want = oblobs.blobs_from_mask(M, area_min=4.0)
+    got = hp.blobs()
+    assert len(want) > 256 and sum(len(w["contour"]) for w in want) > 4096
+    assert len(got) == len(want)
+    for g, w in zip(got, want):
+        assert np.array_equal(g["contour"], w["contour"])
+        assert np.array_equal(g["center"], w["center"])
+    hp.close()
+
+
 def test_blob_capacity_overflow_is_reported():
     from pygofpid_b200._native import GofpidError
     H, W = 64, 64

@@ -81,7 +81,7 @@ def main(raw, srcsv, sass, pattern, srcdir):
     for k, c in byreg.most_common(14):
         print('%5.1f%% %5.1f%%  %s' % (100 * c / tot, 100 * sreg[k] / ts, k))
     print('--- top lines')
-    for loc, c in byline.most_common(24):
+    for loc, c in byline.most_common(70):
         if loc:
             print('%5.1f%% %5.1f%% %s:%d  %s' % (100 * c / tot, 100 * bys[loc] / ts, loc[0], loc[1], text(loc)))
 
