@@ -49,6 +49,10 @@ enum { GOFPID_BLUR_NONE = 0, GOFPID_BLUR_GAUSSIAN = 1, GOFPID_BLUR_BOX = 2 };
 enum { GOFPID_DETECT_FD = 0, GOFPID_DETECT_MOG2 = 1, GOFPID_DETECT_KNN = 2 };
 enum { GOFPID_MORPH_ERODE = 0, GOFPID_MORPH_DILATE = 1 };
 
+#define GOFPID_CONVERT_NONE 0
+#define GOFPID_CONVERT_BGR2GRAY 1 /* cv.COLOR_BGR2GRAY */
+#define GOFPID_CONVERT_RGB2GRAY 2 /* cv.COLOR_RGB2GRAY */
+
 #define GOFPID_MAX_MORPH_OPS 8
 #define GOFPID_MAX_KSIZE 31 /* largest blur kernel side the fused kernel stages in smem */
 #define GOFPID_MAX_SE 31    /* largest structuring-element side                          */
@@ -107,6 +111,11 @@ typedef struct gofpid_config {
     int32_t max_blobs;     /* capacity: connected components per frame  */
     int32_t max_kept;      /* capacity: blobs that pass the area filter */
     int32_t max_points;    /* capacity: contour points per frame        */
+
+    /* colour conversion before the blur: pipeline.py:458-459.  Frames have 3 interleaved channels,
+     * the path works on their gray value (cv.cvtColor's 15-bit fixed point), computed while the
+     * frame is loaded.  The pipeline is created with C = 3. */
+    int32_t convert;       /* GOFPID_CONVERT_* */
 } gofpid_config;
 
 /* One blob that passed the area filter (the device-side half of GOFPID._create_blob,

@@ -47,6 +47,7 @@ class Config(ct.Structure):
         ("find_blobs", ct.c_int32),
         ("blob_area_min", ct.c_double),
         ("max_blobs", ct.c_int32), ("max_kept", ct.c_int32), ("max_points", ct.c_int32),
+        ("convert", ct.c_int32),
     ]
 
 

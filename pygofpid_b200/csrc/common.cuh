@@ -55,6 +55,11 @@ struct BlurParams {
     int box_d, box_delta, box_scale; // box normalisation (see detect.cu)
     uint16_t qx[GOFPID_MAX_KSIZE + 1];
     uint16_t qy[GOFPID_MAX_KSIZE + 1];
+    // colour -> gray fused into the frame load (cv.cvtColor COLOR_BGR2GRAY / COLOR_RGB2GRAY of
+    // pipeline.py:458-459): the source has 3 interleaved channels, the kernels work on 1;
+    // gray = (c0*cw[0] + c1*cw[1] + c2*cw[2] + 2^14) >> 15, OpenCV's 15-bit fixed point
+    int conv;        // 0: frames already have the model's channel count
+    uint32_t cw[3];
 };
 int make_blur_params(int kind, int kw, int kh, double sigma, BlurParams *bp);
 int gaussian_taps_q8(int n, double sigma, uint16_t *q);
@@ -191,6 +196,7 @@ struct MorphPlan {
     // (ascending), so the chain runs on n_levels one-bit threshold planes, 32 pixels per word
     int n_levels;                       // 0: byte path
     int levels[3];
+    int bit_sel[3];                     // bit of the byte that IS threshold plane i (-1: compare bytes)
     int bit_tile_h, bit_hw_l, bit_hw_r; // tile rows, halo words left / right (tile width = 256 px)
     int bit_pad;                        // spare rows above / below the staged rows in shared memory
     size_t bit_smem_bytes;

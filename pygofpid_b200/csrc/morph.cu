@@ -422,6 +422,16 @@ void morph_plan_set_levels(MorphPlan *plan, const int *levels, int n_levels)
     plan->bit_pad = pad + MB_R_PAD;
     plan->bit_smem_bytes = 2 * (size_t)n_levels * (rows + 2 * plan->bit_pad) * (nw + 2) * sizeof(uint32_t);
     if (plan->bit_smem_bytes > 160 * 1024) return; // enormous halo: stay on the byte path
+    // A threshold plane is a single bit of the byte when some bit is set in every level at or above
+    // the threshold and clear in every level below it (0 / 127 / 255: bit 0 and bit 7); otherwise the
+    // kernel compares bytes.
+    for (int i = 0; i < n_levels; i++) {
+        int mask = 0xff;
+        for (int j = 0; j < n_levels; j++) mask &= j >= i ? levels[j] : ~levels[j];
+        plan->bit_sel[i] = -1;
+        for (int b = 0; b < 8; b++)
+            if (mask & (1 << b)) { plan->bit_sel[i] = b; break; }
+    }
     plan->n_levels = n_levels;
 }
 
@@ -434,6 +444,12 @@ __device__ __forceinline__ uint32_t spread4(uint32_t n)
 __device__ __forceinline__ uint32_t ge4(uint32_t w, uint32_t t4)
 {
     return ((__vcmpgeu4(w, t4) & 0x80808080u) * 0x00204081u) >> 28;
+}
+
+// 4 bytes -> 4 bits: bit k of byte i -> bit i
+__device__ __forceinline__ uint32_t bit4(uint32_t w, int k)
+{
+    return (((w >> k) & 0x01010101u) * 0x10204080u) >> 28;
 }
 
 // AND (erode) / OR (dilate) of the taps dx0 .. dx0+len-1 of a bit row, for the 32 pixels of word b
@@ -484,7 +500,7 @@ __device__ __forceinline__ uint32_t row_window_k(uint32_t a, uint32_t b, uint32_
 }
 
 constexpr int MB_R = 2;    // output rows per work item (a thread owns MB_R rows of one word column)
-constexpr int MB_MAXI = 4; // work items per thread decoded up front
+constexpr int MB_MAXI = 2; // work items per thread decoded up front
 
 // Shared-memory images are padded: one spare word left and right of every row and `pad` spare
 // rows above and below, so the windows are read without clamping.  Whatever the spare cells
@@ -560,7 +576,6 @@ __device__ __forceinline__ void op_item_dispatch(const MorphOpDev &op, const Mor
     const bool sq = op.is_rect && op.kw == op.kh && (op.kw & 1);
     if (sq && op.kw == 5) op_item<DIL, 5>(op, runs, A, B, it, G, NWP, ident_next);
     else if (sq && op.kw == 3) op_item<DIL, 3>(op, runs, A, B, it, G, NWP, ident_next);
-    else if (sq && op.kw == 7) op_item<DIL, 7>(op, runs, A, B, it, G, NWP, ident_next);
     else op_item<DIL, 0>(op, runs, A, B, it, G, NWP, ident_next);
 }
 
@@ -613,9 +628,13 @@ morph_bits_kernel(MorphPlan plan, ImageU8 src, ImageU8 dst, uint32_t *bitimg, in
                 }
 #pragma unroll
                 for (int l = 0; l < 3; l++)
-                    if (l < nl)
-                        bits[l] |= (ge4(v[0], lv4[l]) | (ge4(v[1], lv4[l]) << 4) | (ge4(v[2], lv4[l]) << 8) |
-                                    (ge4(v[3], lv4[l]) << 12)) << (16 * h);
+                    if (l < nl) {
+                        const int k = plan.bit_sel[l];
+                        uint32_t b16;
+                        if (k >= 0) b16 = bit4(v[0], k) | (bit4(v[1], k) << 4) | (bit4(v[2], k) << 8) | (bit4(v[3], k) << 12);
+                        else b16 = ge4(v[0], lv4[l]) | (ge4(v[1], lv4[l]) << 4) | (ge4(v[2], lv4[l]) << 8) | (ge4(v[3], lv4[l]) << 12);
+                        bits[l] |= b16 << (16 * h);
+                    }
             }
         }
         const int cell = org + r * NWP + w;

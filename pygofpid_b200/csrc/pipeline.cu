@@ -63,7 +63,8 @@ struct FrameSlot {
 struct gofpid_pipeline {
     gofpid_config cfg;
     std::vector<std::vector<uint8_t>> se_copies;
-    int H = 0, W = 0, C = 0, n_streams = 0, device = 0;
+    int H = 0, W = 0, C = 0, n_streams = 0, device = 0; // C: channels the kernels work on
+    int Csrc = 0;                                        // channels of the frames (3 with a gray conversion)
     cudaStream_t stream = nullptr;   // own stage-A stream (host entry points)
     cudaStream_t stream_b[MAX_DEPTH] = {}; // stage B, one per frame slot
     int depth = DEFAULT_DEPTH;            // frame slots in use
@@ -171,6 +172,11 @@ int reset_state(gofpid_pipeline *p)
     FrameTick t;
     memset(&t, 0, sizeof(t));
     t.knn_rng = p->cfg.knn_rng_seed ? p->cfg.knn_rng_seed : 0xffffffffULL;
+    if (p->cfg.detector == GOFPID_DETECT_MOG2) { // learning rate of frame 1 (mog2_kernel prepares the following ones)
+        const long n2 = 2;
+        const double lr = 1.0 / (double)(n2 < p->mog2p.history ? n2 : p->mog2p.history);
+        t.alphaT = (float)lr; t.alpha1 = 1.0f - (float)lr; t.prune = (float)(-lr * (double)p->mog2p.ct);
+    }
     GOFPID_CUDA_TRY(cudaMemcpy(p->d_tick, &t, sizeof(t), cudaMemcpyHostToDevice));
     if (p->cfg.detector == GOFPID_DETECT_MOG2) {
         const size_t nt = (size_t)p->mog2.tiles_x * p->mog2.tiles_y * p->n_streams;
@@ -242,6 +248,11 @@ int build(gofpid_pipeline *p)
     }
     for (auto &e : p->ev) GOFPID_CUDA_TRY(cudaEventCreate(&e));
     GOFPID_TRY(make_blur_params(cfg.blur_kind, cfg.blur_kw, cfg.blur_kh, cfg.blur_sigma, &p->blur));
+    if (cfg.convert != GOFPID_CONVERT_NONE) { // cv.cvtColor u8: B*3735 + G*19235 + R*9798, 15-bit fixed point
+        const bool bgr = cfg.convert == GOFPID_CONVERT_BGR2GRAY;
+        p->blur.conv = 1;
+        p->blur.cw[0] = bgr ? 3735 : 9798; p->blur.cw[1] = 19235; p->blur.cw[2] = bgr ? 9798 : 3735;
+    }
 
     GOFPID_TRY(alloc_zero((void **)&p->d_tick, sizeof(FrameTick)));
     p->mask_pitch = round_up((size_t)W, 128);
@@ -578,7 +589,7 @@ int fetch_results(gofpid_pipeline *p, FrameSlot *F)
 // Host frames -> the slot's staging buffer (asynchronous when the source is pinned), then the step.
 int submit_host(gofpid_pipeline *p, const uint8_t *h_frames, size_t pitch, size_t stream_stride)
 {
-    const size_t row = (size_t)p->W * p->C;
+    const size_t row = (size_t)p->W * p->Csrc;
     if (pitch < row) { set_error("pitch %zu smaller than a row (%zu bytes)", pitch, row); return GOFPID_ERR_INVALID; }
     FrameSlot &F = p->slots[p->frames % p->depth];
     if (!p->frames_pitch) {
@@ -706,7 +717,15 @@ GOFPID_API int gofpid_pipeline_create(const gofpid_config *cfg, int H, int W, in
     gofpid_pipeline *p = new (std::nothrow) gofpid_pipeline();
     if (!p) { set_error("out of host memory"); return GOFPID_ERR_NOMEM; }
     p->cfg = *cfg;
-    p->H = H; p->W = W; p->C = C; p->n_streams = n_streams; p->device = device;
+    p->H = H; p->W = W; p->C = C; p->Csrc = C; p->n_streams = n_streams; p->device = device;
+    if (cfg->convert != GOFPID_CONVERT_NONE) {
+        if ((cfg->convert != GOFPID_CONVERT_BGR2GRAY && cfg->convert != GOFPID_CONVERT_RGB2GRAY) || C != 3) {
+            delete p;
+            set_error("convert must be BGR2GRAY or RGB2GRAY on 3-channel frames (got code %d, C = %d)", cfg->convert, C);
+            return GOFPID_ERR_UNSUPPORTED;
+        }
+        p->C = 1; // the model, masks and blobs are those of the gray image
+    }
     // own the structuring elements
     p->se_copies.resize(cfg->n_morph);
     for (int i = 0; i < cfg->n_morph; i++) {
@@ -753,7 +772,7 @@ GOFPID_API int gofpid_pipeline_process_device(gofpid_pipeline *p, const uint8_t 
 {
     GOFPID_GUARD(p);
     if (!d_frames) { set_error("null frame pointer"); return GOFPID_ERR_INVALID; }
-    if (pitch < (size_t)p->W * p->C) { set_error("pitch %zu smaller than a row (%d bytes)", pitch, p->W * p->C); return GOFPID_ERR_INVALID; }
+    if (pitch < (size_t)p->W * p->Csrc) { set_error("pitch %zu smaller than a row (%d bytes)", pitch, p->W * p->Csrc); return GOFPID_ERR_INVALID; }
     return run_step(p, d_frames, pitch, stream_stride, (cudaStream_t)stream);
 }
 

@@ -54,7 +54,9 @@ class HotPath:
     def __init__(self, shape, blur=("gaussian", (3, 3), 4.0), detector="MOG2", morph=(),
                  area_min=100.0, n_streams=1, device=0, find_blobs=True, fd_threshold=5,
                  knn_seed=0, max_blobs=1 << 16, max_kept=4096, max_points=1 << 20,
-                 detect_shadows=True):
+                 detect_shadows=True, convert=None):
+        """convert: None | 'bgr2gray' | 'rgb2gray' -- frames are (H, W, 3) and the path works on their
+        gray value (cv.cvtColor of pipeline.py:458-459, computed while the frame is loaded)."""
         L = nat.lib()
         if len(shape) == 2:
             H, W, C = int(shape[0]), int(shape[1]), 1
@@ -99,7 +101,10 @@ class HotPath:
         cfg.find_blobs = 1 if find_blobs else 0
         cfg.blob_area_min = float(area_min)
         cfg.max_blobs, cfg.max_kept, cfg.max_points = int(max_blobs), int(max_kept), int(max_points)
+        cfg.convert = {None: 0, "bgr2gray": 1, "rgb2gray": 2}[convert]
+        # self.C: channels of the frames the caller passes (3 with a gray conversion)
         self.H, self.W, self.C, self.n_streams, self.device = H, W, C, int(n_streams), int(device)
+        self.Cm = 1 if convert else C  # channels of the model / state
         self.detector = detector
         self.find_blobs = bool(find_blobs)
         self._h = ct.c_void_p()
@@ -240,7 +245,7 @@ class HotPath:
         n = self.H * self.W
         w = np.empty((self.H, self.W, 5), np.float32)
         v = np.empty((self.H, self.W, 5), np.float32)
-        m = np.empty((self.H, self.W, 5, self.C), np.float32)
+        m = np.empty((self.H, self.W, 5, self.Cm), np.float32)
         k = np.empty((self.H, self.W), np.uint8)
         f32p, u8p = ct.POINTER(ct.c_float), ct.POINTER(ct.c_uint8)
         nat.check(self._L.gofpid_pipeline_mog2_model(self._h, stream, w.ctypes.data_as(f32p),
@@ -250,7 +255,7 @@ class HotPath:
         return w, v, m, k
 
     def knn_model(self, stream=0):
-        s = np.empty((self.H, self.W, 21, self.C + 1), np.uint8)
+        s = np.empty((self.H, self.W, 21, self.Cm + 1), np.uint8)
         idx = np.empty((3, self.H, self.W), np.uint8)
         nxt = np.empty((3, self.H, self.W), np.uint8)
         cnt = np.zeros(3, np.int32)
@@ -262,7 +267,7 @@ class HotPath:
         return s, idx, nxt, cnt, rng.value
 
     def fd_model(self, stream=0):
-        prev = np.empty((self.H, self.W) if self.C == 1 else (self.H, self.W, self.C), np.uint8)
+        prev = np.empty((self.H, self.W) if self.Cm == 1 else (self.H, self.W, self.Cm), np.uint8)
         valid = ct.c_int(0)
         nat.check(self._L.gofpid_pipeline_fd_model(self._h, stream,
                                                    prev.ctypes.data_as(ct.POINTER(ct.c_uint8)),

@@ -288,12 +288,18 @@ class GOFPID():
         elif X.shape != self.input_shape_:
             raise ValueError('Input shape has changed.')
 
-        if self.convert:
+        # BGR / RGB -> gray is fused into the frame load of the GPU path; any other conversion code
+        # (and the host-estimator path) converts on the host first
+        fused = None
+        if self.convert and self._host_estimator is None and X.ndim == 3 and X.shape[2] == 3 \
+                and X.dtype == np.uint8:
+            fused = {_COLOR_BGR2GRAY: "bgr2gray", _COLOR_RGB2GRAY: "rgb2gray"}.get(self.convert)
+        if self.convert and fused is None:
             X = self._convert(X)
 
         # steps 1-4 on the GPU
         if self._host_estimator is None:
-            self._hot_path(X)
+            self._hot_path(X, fused)
         else:
             self._hot_path_host_estimator(X)
 
@@ -310,17 +316,17 @@ class GOFPID():
             raise NotImplementedError("colour conversion code %r needs OpenCV" % (self.convert,))
         return cv.cvtColor(X, self.convert)  # a step before the hot path; other codes stay on cv2
 
-    def _new_engine(self, shape, detector, blur, morph):
+    def _new_engine(self, shape, detector, blur, morph, convert=None):
         from .hotpath import HotPath
         if len(shape) == 3 and shape[2] == 1:
             shape = shape[:2]
         return HotPath(shape, blur=blur, detector=detector, morph=morph, area_min=100.0,
-                       device=self.device, knn_seed=self.knn_seed)
+                       device=self.device, knn_seed=self.knn_seed, convert=convert)
 
-    def _hot_path(self, X):
+    def _hot_path(self, X, convert=None):
         if self._engine is None:
             self._engine = self._new_engine(X.shape, self.frg_detect, self._plan['blur'],
-                                            self._plan['morph'])
+                                            self._plan['morph'], convert)
         self._engine.process(X)
         self._mask_cache = None
         self.blobs_ = self._engine.blobs(anchor=self.post_filter['anchor'])

@@ -132,6 +132,51 @@ def test_fused_blur_detect_morph(det, C):
         assert np.array_equal(got, want), (det, t, int((got != want).sum()))
 
 
+# ----------------------------------------------------------------------------- colour -> gray
+@pytest.mark.parametrize("code", ["bgr2gray", "rgb2gray"])
+@pytest.mark.parametrize("H,W", [(37, 53), (64, 130), (9, 257)])
+@pytest.mark.parametrize("blur", [None, ("gaussian", (3, 3), 4.0), ("gaussian", (7, 7), 0.0), ("box", (5, 5))])
+def test_fused_gray_conversion(code, H, W, blur):
+    """cv.cvtColor(COLOR_BGR2GRAY / COLOR_RGB2GRAY) (pipeline.py:458-459) fused into the frame load:
+    masks and state equal those of the oracle fed with cv2's gray image."""
+    import cv2
+    cvcode = cv2.COLOR_BGR2GRAY if code == "bgr2gray" else cv2.COLOR_RGB2GRAY
+    rs = np.random.RandomState(17)
+    hp = _hot((H, W, 3), blur=blur, detector="FD", find_blobs=False, fd_threshold=5, convert=code)
+    fd = cport.FrameDifferencing(5)
+    base = rs.randint(0, 256, (H, W, 3)).astype(np.uint8)
+    for t in range(5):
+        f = np.clip(base.astype(np.int16) + rs.randint(-9, 10, base.shape), 0, 255).astype(np.uint8)
+        g = cv2.cvtColor(f, cvcode)
+        if blur is None:
+            b = g
+        elif blur[0] == "gaussian":
+            b = cport.gaussian_blur(g, blur[1], blur[2])
+        else:
+            b = cport.box_blur(g, blur[1])
+        want = fd.apply(b)
+        hp.process(f)
+        assert np.array_equal(hp.mask(), want), (code, blur, t)
+        assert np.array_equal(hp.fd_model(), b), (code, blur, t)
+    hp.close()
+
+
+@pytest.mark.parametrize("det", ["MOG2", "KNN"])
+def test_fused_gray_conversion_mixture_models(det):
+    import cv2
+    H, W = 48, 70
+    hp = _hot((H, W, 3), blur=("gaussian", (3, 3), 4.0), detector=det, find_blobs=False, knn_seed=5,
+              convert="bgr2gray")
+    ora = cport.MOG2(H, W, 1) if det == "MOG2" else cport.KNN(H, W, 1, 5)
+    clip = SyntheticClip(H, W, 3, seed=4, n_obj=3)
+    for t in range(30):
+        f = clip.next()
+        want = ora.apply(cport.gaussian_blur(cv2.cvtColor(f, cv2.COLOR_BGR2GRAY), (3, 3), 4.0))
+        hp.process(f)
+        assert np.array_equal(hp.mask(), want), (det, t)
+    hp.close()
+
+
 # ----------------------------------------------------------------------------- blobs
 def _blob_masks():
     import cv2
