@@ -33,10 +33,18 @@ constexpr int CCL_TW = 64;  // one 64-bit word of class bits per tile row
 constexpr int CCL_TH = 32;
 constexpr int CCL_THREADS = 16 * CCL_TH; // each thread owns 4 consecutive pixels of a row
 
-constexpr int TRACE_THREADS = 1024;
-constexpr int TRACE_MAX_CP = 4096;          // checkpoints per contour
-constexpr int TRACE_HT = 8192;              // hash slots (power of two, >= 2 * TRACE_MAX_CP)
-constexpr int TRACE_HT_SHIFT = 19;          // 32 - log2(TRACE_HT)
+// (a 256-thread / 48 KB variant that fits next to resident MOG2 tiles was measured and is no
+// faster: the CTAs are few, and each phase then takes more rounds)
+#ifndef GOFPID_TRACE_THREADS
+#define GOFPID_TRACE_THREADS 1024
+#endif
+#ifndef GOFPID_TRACE_LOG2_CP
+#define GOFPID_TRACE_LOG2_CP 12
+#endif
+constexpr int TRACE_THREADS = GOFPID_TRACE_THREADS;
+constexpr int TRACE_MAX_CP = 1 << GOFPID_TRACE_LOG2_CP;     // checkpoints per contour
+constexpr int TRACE_HT = 2 * TRACE_MAX_CP;                  // hash slots (power of two, >= 2 * TRACE_MAX_CP)
+constexpr int TRACE_HT_SHIFT = 32 - (GOFPID_TRACE_LOG2_CP + 1); // 32 - log2(TRACE_HT)
 // per checkpoint: a00 (8 B) + state, length, two (next, distance) pairs (24 B)
 constexpr size_t TRACE_SMEM_BYTES = (size_t)TRACE_MAX_CP * (8 + 24) + (size_t)TRACE_HT * 8;
 
