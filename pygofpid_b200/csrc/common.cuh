@@ -60,6 +60,8 @@ struct BlurParams {
     // gray = (c0*cw[0] + c1*cw[1] + c2*cw[2] + 2^14) >> 15, OpenCV's 15-bit fixed point
     int conv;        // 0: frames already have the model's channel count
     uint32_t cw[3];
+    // 3x3 kernels whose taps fit a byte: the taps packed for dp4a (0: not available)
+    uint32_t qx3, qy3;
 };
 int make_blur_params(int kind, int kw, int kh, double sigma, BlurParams *bp);
 int gaussian_taps_q8(int n, double sigma, uint16_t *q);

@@ -75,6 +75,30 @@ def test_mog2_masks_and_model_bitexact(H, W, C, sigma):
     assert abs(hp.mog2_mean_modes() - ok.mean()) < 1e-9
 
 
+@pytest.mark.parametrize("blur", [("gaussian", (3, 3), 4.0), ("gaussian", (3, 3), 0.0), ("box", (3, 3)),
+                                  ("gaussian", (3, 3), 0.05)])
+@pytest.mark.parametrize("H,W", [(40, 260), (41, 331)])
+def test_mog2_fused_blur_interior_and_border_tiles(blur, H, W):
+    """Frames wide and tall enough to have INTERIOR 64x8 tiles (3x3 blur evaluated in registers with
+    dp4a) next to border tiles (general shared-memory path): blurred state and masks bit-exact.
+    sigma 0.05 gives the taps [0, 256, 0], which do not fit a byte and must take the general path."""
+    hp = _hot((H, W), blur=blur, detector="MOG2", morph=(), find_blobs=False)
+    ora = cport.MOG2(H, W, 1)
+    clip = SyntheticClip(H, W, 1, seed=77, n_obj=4, noise_sigma=5)
+    for t in range(40):
+        f = clip.next()
+        b = cport.gaussian_blur(f, blur[1], blur[2]) if blur[0] == "gaussian" else cport.box_blur(f, blur[1])
+        want = ora.apply(b)
+        hp.process(f)
+        got = hp.mask()
+        assert np.array_equal(got, want), (blur, t, int((got != want).sum()))
+    w, v, m, k = hp.mog2_model()
+    ow, ov, om, ok = ora.planes()
+    live = np.arange(5)[None, None, :] < ok[..., None]
+    assert np.array_equal(k, ok) and np.array_equal(m[live], om[live]) and np.array_equal(v[live], ov[live])
+    hp.close()
+
+
 def test_mog2_first_frame_is_shadow_everywhere():
     hp = _hot((32, 40), blur=None, detector="MOG2", find_blobs=False)
     f = np.full((32, 40), 90, np.uint8)
