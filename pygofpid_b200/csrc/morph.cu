@@ -392,9 +392,18 @@ morph_chain_kernel(MorphPlan plan, ImageU8 src, ImageU8 dst, int H, int W)
 // grey-level result is rebuilt from the planes on the way out.  A CTA owns 256 x tile_h pixels,
 // stages tile + accumulated halo (whole halo WORDS left and right) as bits, and also emits the
 // foreground bit image the blob stage works on.
-constexpr int MB_THREADS = 512;
-constexpr int MB_TWW = 8; // tile width in 32-pixel words
-constexpr int MB_R_PAD = 2; // spare rows for the last, partial block of output rows (>= MB_R - 1)
+#ifndef GOFPID_MB_THREADS
+#define GOFPID_MB_THREADS 256
+#endif
+#ifndef GOFPID_MB_TWW
+#define GOFPID_MB_TWW 8
+#endif
+#ifndef GOFPID_MB_R
+#define GOFPID_MB_R 4
+#endif
+constexpr int MB_THREADS = GOFPID_MB_THREADS;
+constexpr int MB_TWW = GOFPID_MB_TWW; // tile width in 32-pixel words
+constexpr int MB_R_PAD = 4; // spare rows for the last, partial block of output rows (>= MB_R - 1)
 
 void morph_plan_set_levels(MorphPlan *plan, const int *levels, int n_levels)
 {
@@ -499,7 +508,7 @@ __device__ __forceinline__ uint32_t row_window_k(uint32_t a, uint32_t b, uint32_
     return acc;
 }
 
-constexpr int MB_R = 2;    // output rows per work item (a thread owns MB_R rows of one word column)
+constexpr int MB_R = GOFPID_MB_R;    // output rows per work item (a thread owns MB_R rows of one word column)
 constexpr int MB_MAXI = 2; // work items per thread decoded up front
 
 // Shared-memory images are padded: one spare word left and right of every row and `pad` spare

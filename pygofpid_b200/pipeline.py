@@ -395,6 +395,25 @@ class GOFPID():
         dy = blob['center'][1] - tracked['center'][1]
         return dx**2 / r_maj**2 + dy**2 / r_min**2
 
+    def _tracking_distance_matrix(self, tracks, blobs):
+        """`_tracking_distance` for every (blob, track) pair at once.  Array arithmetic in the very
+        dtypes the reference's scalar code runs in (int16 centre differences and squares, wrapping
+        like the scalars do; int32 radii; float64 quotients), so the matrix is identical to the
+        double loop -- which costs ~130 ms per frame at 200 blobs."""
+        tb = np.array([t['bottom'][1] for t in tracks])
+        tc = np.array([t['center'] for t in tracks]).reshape(len(tracks), 2)
+        bc = np.array([b['center'] for b in blobs]).reshape(len(blobs), 2)
+        if tc.dtype != np.int16 or bc.dtype != np.int16:  # foreign blob dicts: stay on the scalar path
+            return np.array([[self._tracking_distance(t, b) for t in tracks] for b in blobs], dtype=np.float64)
+        major = (self._predict_perspective('height', tb) * self.tracking['factor']).astype(np.int32)
+        minor = (major / 2).astype(np.int32)
+        ok = (major > 0) & (minor > 0)
+        with np.errstate(over='ignore', divide='ignore', invalid='ignore'):
+            dx = bc[:, None, 0] - tc[None, :, 0]
+            dy = bc[:, None, 1] - tc[None, :, 1]
+            d = dx**2 / (major**2)[None, :] + dy**2 / (minor**2)[None, :]
+        return np.where(ok[None, :], d, 0.0)
+
     @staticmethod
     def _new_track(blob):
         return {'contour': blob['contour'].copy(), 'anchor': blob['anchor'], 'bottom': blob['bottom'],
@@ -440,8 +459,7 @@ class GOFPID():
             for j in range(n_tracks - 1, -1, -1):
                 self._miss(j)
             return
-        dist = np.array([[self._tracking_distance(tracks[j], b) for j in range(n_tracks)]
-                         for b in blobs], dtype=np.float64)
+        dist = self._tracking_distance_matrix(tracks, blobs)
         for i, blob in enumerate(blobs):
             j = int(np.argmin(dist[i]))
             if dist[i, j] <= 1:

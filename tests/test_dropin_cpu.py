@@ -139,3 +139,27 @@ def test_point_in_polygon_matches_cv2():
     for _ in range(2000):
         p = (int(rs.randint(0, 45)), int(rs.randint(0, 35)))
         assert h.point_in_polygon(poly, p) == cv.pointPolygonTest(poly, p, False)
+
+
+def test_tracking_distance_matrix_equals_the_scalar_code():
+    """The vectorised (blob, track) distance matrix of the tracking tail (reference
+    pipeline.py:590-662) reproduces the scalar code value for value, int16 wrap-around included."""
+    import warnings
+    from pygofpid_b200.pipeline import GOFPID
+    g = GOFPID.__new__(GOFPID)
+    g.input_shape_ = (1080, 1920)
+    g.tracking = {'factor': 1.5}
+    g._perspective = {'height': np.clip(np.linspace(-20, 300, 1080), 0, None)}
+    rs = np.random.RandomState(0)
+    with warnings.catch_warnings():
+        warnings.simplefilter('ignore')
+        for trial in range(10):
+            nt, nb = rs.randint(1, 40), rs.randint(1, 40)
+            tracks = [{'bottom': np.array([rs.randint(0, 1920), rs.randint(-5, 1100)], np.int16),
+                       'center': np.array([rs.randint(0, 1920), rs.randint(0, 1080)], np.int16)}
+                      for _ in range(nt)]
+            blobs = [{'center': np.array([rs.randint(0, 1920), rs.randint(0, 1080)], np.int16)}
+                     for _ in range(nb)]
+            want = np.array([[g._tracking_distance(t, b) for t in tracks] for b in blobs], dtype=np.float64)
+            got = g._tracking_distance_matrix(tracks, blobs)
+            assert np.array_equal(got, want, equal_nan=True), trial
