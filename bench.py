@@ -289,7 +289,7 @@ def main():
     w0 = time.perf_counter()
     d2h = 0
     nblobs = 0
-    LAG = 3  # frames submitted ahead of the one whose results are collected (4 frames in flight)
+    LAG = hp.depth - 1  # frames submitted ahead of the one whose results are collected
     for i in range(e2e_frames + LAG):
         if i < e2e_frames:
             t = (t_idx + i) % n_clip
@@ -297,12 +297,25 @@ def main():
         if i >= LAG:
             hp.select(min(i, e2e_frames - 1) - (i - LAG))
             for z in range(S):
-                recs, pts = hp.raw_blobs(z)
+                recs, pts = hp.raw_blobs(z, copy=False)
                 nblobs += len(recs)
                 d2h += 32 + len(recs) * 56 + pts.shape[0] * 8
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - w0
     t_idx += e2e_frames
+
+    # ---- the same end-to-end work through the clip entry point (one library call for a whole
+    # clip in pinned host memory: gofpid_pipeline_process_host_sequence) -------------------------
+    seq_frames = min(n_clip, e2e_frames)
+    seq_fps = None
+    if n_clip >= 8:
+        hp.process_sequence(pinned[:8])  # untimed: sizes the output buffers
+        barrier()
+        w0 = time.perf_counter()
+        counts, _, _ = hp.process_sequence(pinned[:seq_frames])
+        torch.cuda.synchronize()
+        seq_s = time.perf_counter() - w0
+        seq_fps = seq_frames * S / seq_s
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-kernel time of the dominant kernel (CUDA events around it, same steps) --------
@@ -357,8 +370,12 @@ def main():
                     "d2h_bytes_per_step": int(d2h / max(e2e_frames, 1) * F), "frames": e2e_frames,
                     "mpix_per_s": e2e_fps * mpix,
                     "blobs_per_frame": nblobs / max(e2e_frames * S, 1),
+                    "clip_call": None if seq_fps is None else {
+                        "value": seq_fps * world, "unit": "frames/s", "frames": seq_frames,
+                        "api": "gofpid_pipeline_process_host_sequence (one call per clip of pinned host frames, "
+                               "blob lists of every frame out)"},
                     "api": "gofpid_pipeline_submit_host + gofpid_pipeline_select + gofpid_pipeline_blobs "
-                           "(pinned host frames in, blob lists with contours out, 4 frames in flight)"},
+                           "(pinned host frames in, blob lists with contours out, %d frames in flight)" % hp.depth},
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic_per_launch(kname),

@@ -175,15 +175,29 @@ GOFPID_API int gofpid_pipeline_process_device(gofpid_pipeline *p, const uint8_t 
 GOFPID_API int gofpid_pipeline_process_host(gofpid_pipeline *p, const uint8_t *h_frames,
                                             size_t pitch, size_t stream_stride);
 
+/* A clip of n_frames time steps in host memory (frame t at h_frames + t * frame_stride; examples/
+ * video.py's read-detect loop over a decoded file) in ONE call: frames are submitted ahead of the
+ * one whose blobs are being collected, as a caller of submit_host / select / blobs would do.
+ * Blob records and contour points of all frames are appended to h_blobs / h_points (point_offset
+ * restarts at 0 for every frame and stream); h_counts[(t * n_streams + z) * 2 + {0, 1}] receives
+ * the blob and point count of frame t, stream z.  h_blobs and h_points may be NULL (counts only). */
+GOFPID_API int gofpid_pipeline_process_host_sequence(gofpid_pipeline *p, const uint8_t *h_frames,
+                                                     int n_frames, size_t frame_stride, size_t pitch,
+                                                     size_t stream_stride, gofpid_blob *h_blobs,
+                                                     int blob_capacity, int32_t *h_points,
+                                                     int point_capacity, int32_t *h_counts);
+
 /* Asynchronous variant of process_host for pinned host frames: enqueues the host->device copy
- * and the step and returns; up to two frames are in flight (labelling / tracing of frame t
- * overlaps the model update of frame t+1).  Results are collected later with the getters
- * below, after gofpid_pipeline_select(p, 1) for the frame before the newest one. */
+ * and the step and returns; several frames are in flight (morphology / labelling / tracing of
+ * frames t, t-1, ... overlap the model update of frame t+1).  Results are collected later with
+ * the getters below, after gofpid_pipeline_select(p, age) for an earlier frame. */
 GOFPID_API int gofpid_pipeline_submit_host(gofpid_pipeline *p, const uint8_t *h_frames,
                                            size_t pitch, size_t stream_stride);
 /* Which frame the result getters refer to: age 0 = newest submitted frame (default after every
- * process/submit call), 1 = the one before it. */
+ * process/submit call), 1 = the one before it, ... up to the pipeline depth - 1 (3). */
 GOFPID_API int gofpid_pipeline_select(gofpid_pipeline *p, int age);
+/* Frame slots of the handle = frames that can be in flight (submit_host) at once. */
+GOFPID_API int gofpid_pipeline_depth(gofpid_pipeline *p);
 
 /* Results of the selected frame (host copies; these wait for that frame's kernels). */
 GOFPID_API int gofpid_pipeline_frame_info(gofpid_pipeline *p, int stream_idx,

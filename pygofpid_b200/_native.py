@@ -84,7 +84,10 @@ SIGNATURES = {
     "gofpid_pipeline_process_device": (ct.c_int, [_vp, _vp, _sz, _sz, _vp]),
     "gofpid_pipeline_process_host": (ct.c_int, [_vp, _vp, _sz, _sz]),
     "gofpid_pipeline_submit_host": (ct.c_int, [_vp, _vp, _sz, _sz]),
+    "gofpid_pipeline_process_host_sequence": (ct.c_int, [_vp, _vp, ct.c_int, _sz, _sz, _sz, ct.POINTER(Blob), ct.c_int,
+                                                         ct.POINTER(ct.c_int32), ct.c_int, ct.POINTER(ct.c_int32)]),
     "gofpid_pipeline_select": (ct.c_int, [_vp, ct.c_int]),
+    "gofpid_pipeline_depth": (ct.c_int, [_vp]),
     "gofpid_pipeline_frame_info": (ct.c_int, [_vp, ct.c_int, ct.POINTER(FrameInfo)]),
     "gofpid_pipeline_blobs": (ct.c_int, [_vp, ct.c_int, ct.POINTER(Blob), ct.c_int, _i32p, ct.c_int,
                                          ct.POINTER(ct.c_int), ct.POINTER(ct.c_int)]),

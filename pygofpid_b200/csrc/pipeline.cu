@@ -36,8 +36,10 @@ using namespace gofpid;
 // sequential; stage B only needs the finished mask of its own frame and occupies a handful of
 // SMs (one CTA per stream or per blob), so consecutive frames of ONE camera stream overlap and
 // the frame rate is set by stage A alone.
-constexpr int MAX_DEPTH = 6;
-constexpr int DEFAULT_DEPTH = 4; // GOFPID_DEPTH overrides (1 .. MAX_DEPTH)
+constexpr int MAX_DEPTH = 8;
+constexpr int DEFAULT_DEPTH = 6;       // few camera streams per handle: deep, stage B latency is several stage As
+constexpr int DEFAULT_DEPTH_MANY = 4;  // many streams per handle: every kernel is already wide, slots cost memory
+// (GOFPID_DEPTH overrides: 1 .. MAX_DEPTH)
 
 struct FrameSlot {
     uint8_t *d_final = nullptr;   // final mask of the frame in this slot
@@ -92,6 +94,7 @@ struct gofpid_pipeline {
     int selected = 0; // age of the frame the result getters refer to (0 newest, 1 previous)
 
     size_t frames_pitch = 0, frames_stream = 0;
+    const uint8_t *pinned_lo = nullptr, *pinned_hi = nullptr; // host range last found to be page-locked
     uint8_t *h_frames = nullptr; // pinned staging for pageable input
 
     bool profiling = false;
@@ -235,6 +238,7 @@ int build(gofpid_pipeline *p)
     for (cudaStream_t *s : {&p->stream, &p->stream_c, &p->stream_h})
         GOFPID_CUDA_TRY(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking));
     {
+        p->depth = p->n_streams <= 8 ? DEFAULT_DEPTH : DEFAULT_DEPTH_MANY;
         const char *e = getenv("GOFPID_DEPTH");
         if (e && atoi(e) >= 1 && atoi(e) <= MAX_DEPTH) p->depth = atoi(e);
         // stage B runs at a higher priority than stage A: its few CTAs take the SMs they need as soon
@@ -599,10 +603,16 @@ int submit_host(gofpid_pipeline *p, const uint8_t *h_frames, size_t pitch, size_
     if (!F.d_frames)
         for (int si = 0; si < p->depth; si++) // (all slots at once: no allocation inside a running pipeline)
             if (!p->slots[si].d_frames) GOFPID_CUDA_TRY(cudaMalloc(&p->slots[si].d_frames, p->frames_stream * p->n_streams));
-    cudaPointerAttributes attr;
-    bool pinned = false;
-    if (cudaPointerGetAttributes(&attr, h_frames) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
-    else cudaGetLastError();
+    bool pinned = h_frames >= p->pinned_lo && h_frames < p->pinned_hi;
+    if (!pinned) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, h_frames) == cudaSuccess) pinned = attr.type == cudaMemoryTypeHost;
+        else cudaGetLastError();
+        if (pinned) { // remember the frame's own bytes: clips are usually one allocation walked frame by frame
+            p->pinned_lo = h_frames;
+            p->pinned_hi = h_frames + (p->n_streams > 1 ? stream_stride * (size_t)p->n_streams : pitch * (size_t)p->H);
+        }
+    }
     const uint8_t *src = h_frames;
     size_t spitch = pitch, sstride = stream_stride;
     cudaStream_t sh = p->stream_h;
@@ -791,6 +801,44 @@ GOFPID_API int gofpid_pipeline_process_host(gofpid_pipeline *p, const uint8_t *h
     if (!h_frames) { set_error("null frame pointer"); return GOFPID_ERR_INVALID; }
     GOFPID_TRY(submit_host(p, h_frames, pitch, stream_stride));
     return fetch_results(p, selected_slot(p));
+}
+
+// A whole clip in one call: the pipelined loop (submit frame t, collect frame t - lag) that a
+// caller of submit_host / select / blobs would write, without the per-call overhead.
+GOFPID_API int gofpid_pipeline_process_host_sequence(gofpid_pipeline *p, const uint8_t *h_frames, int n_frames,
+                                                     size_t frame_stride, size_t pitch, size_t stream_stride,
+                                                     gofpid_blob *h_blobs, int blob_capacity, int32_t *h_points,
+                                                     int point_capacity, int32_t *h_counts)
+{
+    GOFPID_GUARD(p);
+    if (!h_frames || n_frames < 0 || !h_counts) { set_error("bad argument"); return GOFPID_ERR_INVALID; }
+    if (!p->cfg.find_blobs) { set_error("pipeline was created with find_blobs = 0"); return GOFPID_ERR_INVALID; }
+    const int lag = p->depth - 1, S = p->n_streams;
+    int nb_total = 0, np_total = 0;
+    for (int t = 0; t < n_frames + lag; t++) {
+        if (t < n_frames) GOFPID_TRY(submit_host(p, h_frames + (size_t)t * frame_stride, pitch, stream_stride));
+        const int c = t - lag; // frame to collect
+        if (c < 0) continue;
+        const int newest = t < n_frames ? t : n_frames - 1;
+        p->selected = newest - c;
+        for (int z = 0; z < S; z++) {
+            int nb = 0, np = 0;
+            const int rc = gofpid_pipeline_blobs(p, z, h_blobs ? h_blobs + nb_total : nullptr, blob_capacity - nb_total,
+                                                 h_points ? h_points + (size_t)np_total * 2 : nullptr,
+                                                 point_capacity - np_total, &nb, &np);
+            if (rc != GOFPID_OK) { p->selected = 0; return rc; }
+            h_counts[((size_t)c * S + z) * 2] = nb;
+            h_counts[((size_t)c * S + z) * 2 + 1] = np;
+            if (h_blobs || h_points) { nb_total += nb; np_total += np; }
+        }
+    }
+    p->selected = 0;
+    return GOFPID_OK;
+}
+
+GOFPID_API int gofpid_pipeline_depth(gofpid_pipeline *p)
+{
+    return p ? p->depth : 0;
 }
 
 GOFPID_API int gofpid_pipeline_select(gofpid_pipeline *p, int age)

@@ -34,6 +34,11 @@ def gaussian_taps_q8(n, sigma):
     return np.array(q[:int(n)], dtype=np.uint16)
 
 
+# numpy view of gofpid_blob (include/gofpid_b200.h)
+BLOB_DTYPE = np.dtype([(n, '<i4') for n in ('first', 'x0', 'y0', 'x1', 'y1', 'area_px', 'n_points', 'point_offset',
+                                              'nested', 'reserved')] + [(n, '<i8') for n in ('a00', 'a10', 'a01')])
+
+
 class HotPath:
     """One CUDA pipeline for `n_streams` camera streams of shape (H, W[, C]).
 
@@ -159,6 +164,11 @@ class HotPath:
         Up to three frames are in flight; collect results with select(age) + the getters."""
         nat.check(self._L.gofpid_pipeline_submit_host(self._h, ptr, pitch, stream_stride))
 
+    @property
+    def depth(self):
+        """Frame slots of the handle: frames that can be in flight at once (submit_pinned)."""
+        return int(self._L.gofpid_pipeline_depth(self._h))
+
     def select(self, age=0):
         """Result getters refer to the newest frame (age 0) or the ones before it (age 1, 2)."""
         nat.check(self._L.gofpid_pipeline_select(self._h, age))
@@ -197,26 +207,64 @@ class HotPath:
         return {int(r[0]) + 1: dict(area=int(r[5]), x0=int(r[1]), y0=int(r[2]), x1=int(r[3]), y1=int(r[4]))
                 for r in buf[:n.value]}
 
-    def raw_blobs(self, stream=0):
+    def raw_blobs(self, stream=0, copy=True):
         """(records, points): structured blob records in the reference's order and one
         (n_points, 2) int32 array of contour points.
 
-        One library call into reusable buffers sized for a normal frame; a busier frame (the call
-        reports the sizes it needs) is fetched again into buffers of that size."""
+        One library call into buffers the handle keeps (sized for a normal frame; a busier frame
+        -- the call reports the sizes it needs -- grows them).  copy=False returns views of those
+        buffers, valid until the next call."""
         nb, npt = ct.c_int(0), ct.c_int(0)
-        cap_b, cap_p = getattr(self, "_blob_cap", (64, 8192))
         while True:
-            recs = (nat.Blob * cap_b)()
-            pts = np.empty((cap_p, 2), np.int32)
-            rc = self._L.gofpid_pipeline_blobs(self._h, stream, recs, cap_b,
-                                               pts.ctypes.data_as(ct.POINTER(ct.c_int32)), cap_p,
+            buf = getattr(self, "_blob_buf", None)
+            if buf is None:
+                buf = self._blob_buf = ((nat.Blob * 64)(), np.empty((8192, 2), np.int32))
+            recs, pts = buf
+            rc = self._L.gofpid_pipeline_blobs(self._h, stream, recs, len(recs),
+                                               pts.ctypes.data_as(ct.POINTER(ct.c_int32)), pts.shape[0],
                                                ct.byref(nb), ct.byref(npt))
-            if rc == nat.ERR_INVALID and (nb.value > cap_b or npt.value > cap_p):
-                cap_b, cap_p = max(cap_b, 2 * nb.value), max(cap_p, 2 * npt.value)
-                self._blob_cap = (cap_b, cap_p)
+            if rc == nat.ERR_INVALID and (nb.value > len(recs) or npt.value > pts.shape[0]):
+                self._blob_buf = ((nat.Blob * max(len(recs), 2 * nb.value))(),
+                                  np.empty((max(pts.shape[0], 2 * npt.value), 2), np.int32))
                 continue
             nat.check(rc)
-            return recs[:nb.value], pts[:npt.value]
+            out = pts[:npt.value]
+            return recs[:nb.value], (out.copy() if copy else out)
+
+    def process_sequence(self, frames, blob_capacity=None, point_capacity=None):
+        """A whole clip from HOST memory in one library call (gofpid_pipeline_process_host_sequence):
+        frames (T, H, W[, C]) for one stream or (T, n_streams, H, W[, C]).  Returns (counts, records,
+        points): counts[t, z] = (blobs, points) of frame t / stream z, records a numpy structured
+        array (fields of gofpid_blob) and points (n, 2) int32, both in frame order."""
+        per = (self.H, self.W) if self.C == 1 else (self.H, self.W, self.C)
+        if hasattr(frames, "data_ptr"):  # a (pinned) torch uint8 tensor: used in place
+            if not frames.is_contiguous() or frames.element_size() != 1:
+                raise TypeError("frames must be a contiguous uint8 tensor")
+            shape, ptr, keep = tuple(frames.shape), frames.data_ptr(), frames
+        else:
+            keep = np.ascontiguousarray(frames, dtype=np.uint8)
+            shape, ptr = keep.shape, keep.ctypes.data
+        if shape[1:] == per and self.n_streams == 1:
+            shape = (shape[0], 1) + per
+        if shape[1:] != (self.n_streams,) + per:
+            raise ValueError("Input shape has changed.")
+        T = shape[0]
+        row = self.W * self.C
+        bc = int(blob_capacity or 64 * T * self.n_streams)
+        pc = int(point_capacity or 8192 * T * self.n_streams)
+        counts = np.zeros((T, self.n_streams, 2), np.int32)
+        while True:
+            recs = np.zeros(bc, BLOB_DTYPE)
+            pts = np.empty((pc, 2), np.int32)
+            rc = self._L.gofpid_pipeline_process_host_sequence(
+                self._h, ptr, T, row * self.H * self.n_streams, row, row * self.H,
+                recs.ctypes.data_as(ct.POINTER(nat.Blob)), bc, pts.ctypes.data_as(ct.POINTER(ct.c_int32)), pc,
+                counts.ctypes.data_as(ct.POINTER(ct.c_int32)))
+            if rc == nat.ERR_INVALID and "capacity" in nat.last_error():
+                raise ValueError("blob_capacity / point_capacity too small for this clip: " + nat.last_error())
+            nat.check(rc)
+            nb, npt = int(counts[..., 0].sum()), int(counts[..., 1].sum())
+            return counts, recs[:nb], pts[:npt]
 
     def blobs(self, stream=0, anchor="bottom"):
         """self.blobs_ of the reference (pipeline.py:555-588): list of dicts with keys

@@ -324,6 +324,31 @@ def test_busy_frame_beyond_the_prefetched_result_prefix():
     hp.close()
 
 
+def test_sequence_call_equals_frame_by_frame_calls():
+    """gofpid_pipeline_process_host_sequence (a clip in one call, frames in flight) gives the blob
+    lists of the frame-by-frame calls, frame for frame."""
+    H, W = 96, 160
+    r3 = np.ones((3, 3), np.uint8)
+    kw = dict(blur=("gaussian", (3, 3), 4.0), detector="MOG2", morph=[("erode", r3), ("dilate", r3)], area_min=20.0)
+    clip = np.stack(SyntheticClip(H, W, 1, seed=3, n_obj=5).frames(25))
+    a, b = _hot((H, W), **kw), _hot((H, W), **kw)
+    counts, recs, pts = a.process_sequence(clip)
+    assert counts.shape == (25, 1, 2)
+    ob = op = 0
+    for t in range(25):
+        b.process(clip[t])
+        want_recs, want_pts = b.raw_blobs()
+        nb, npt = counts[t, 0]
+        assert nb == len(want_recs) and npt == len(want_pts), t
+        assert np.array_equal(pts[op:op + npt], want_pts), t
+        for k in range(nb):
+            for f in ("first", "x0", "y0", "x1", "y1", "area_px", "n_points", "point_offset", "a00", "a10", "a01"):
+                assert recs[ob + k][f] == getattr(want_recs[k], f), (t, k, f)
+        ob += nb; op += npt
+    assert ob == len(recs) and op == len(pts)
+    a.close(); b.close()
+
+
 def test_blob_capacity_overflow_is_reported():
     from pygofpid_b200._native import GofpidError
     H, W = 64, 64
