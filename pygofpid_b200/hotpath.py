@@ -250,21 +250,23 @@ class HotPath:
             raise ValueError("Input shape has changed.")
         T = shape[0]
         row = self.W * self.C
-        bc = int(blob_capacity or 64 * T * self.n_streams)
-        pc = int(point_capacity or 8192 * T * self.n_streams)
+        # default capacities: 256 blobs and 8 (H + W) contour points per frame and stream (what travels
+        # to the host with every step); a clip that needs more raises ValueError -- the temporal model
+        # has advanced by then, so size generously or reset()
+        bc = int(blob_capacity or 256 * T * self.n_streams)
+        pc = int(point_capacity or max(4096, 8 * (self.H + self.W)) * T * self.n_streams)
         counts = np.zeros((T, self.n_streams, 2), np.int32)
-        while True:
-            recs = np.zeros(bc, BLOB_DTYPE)
-            pts = np.empty((pc, 2), np.int32)
-            rc = self._L.gofpid_pipeline_process_host_sequence(
-                self._h, ptr, T, row * self.H * self.n_streams, row, row * self.H,
-                recs.ctypes.data_as(ct.POINTER(nat.Blob)), bc, pts.ctypes.data_as(ct.POINTER(ct.c_int32)), pc,
-                counts.ctypes.data_as(ct.POINTER(ct.c_int32)))
-            if rc == nat.ERR_INVALID and "capacity" in nat.last_error():
-                raise ValueError("blob_capacity / point_capacity too small for this clip: " + nat.last_error())
-            nat.check(rc)
-            nb, npt = int(counts[..., 0].sum()), int(counts[..., 1].sum())
-            return counts, recs[:nb], pts[:npt]
+        recs = np.empty(bc, BLOB_DTYPE)
+        pts = np.empty((pc, 2), np.int32)
+        rc = self._L.gofpid_pipeline_process_host_sequence(
+            self._h, ptr, T, row * self.H * self.n_streams, row, row * self.H,
+            recs.ctypes.data_as(ct.POINTER(nat.Blob)), bc, pts.ctypes.data_as(ct.POINTER(ct.c_int32)), pc,
+            counts.ctypes.data_as(ct.POINTER(ct.c_int32)))
+        if rc == nat.ERR_INVALID and "capacity" in nat.last_error():
+            raise ValueError("blob_capacity / point_capacity too small for this clip: " + nat.last_error())
+        nat.check(rc)
+        nb, npt = int(counts[..., 0].sum()), int(counts[..., 1].sum())
+        return counts, recs[:nb], pts[:npt]
 
     def blobs(self, stream=0, anchor="bottom"):
         """self.blobs_ of the reference (pipeline.py:555-588): list of dicts with keys
