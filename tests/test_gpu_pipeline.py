@@ -114,8 +114,15 @@ def test_mog2_first_frame_is_shadow_everywhere():
 
 
 # ----------------------------------------------------------------------------- KNN
-@pytest.mark.parametrize("H,W,C", [(37, 53, 1), (37, 53, 3), (50, 66, 1), (64, 128, 1)])
-def test_knn_masks_and_state_bitexact(H, W, C):
+@pytest.mark.parametrize("kernel", ["default", "scalar"])
+@pytest.mark.parametrize("H,W,C", [(37, 53, 1), (37, 53, 3), (50, 66, 1), (64, 128, 1), (40, 258, 1)])
+def test_knn_masks_and_state_bitexact(H, W, C, kernel, monkeypatch):
+    """Gray frames run the byte-SIMD kernel (knn_gray_kernel) by default; kernel="scalar" forces the
+    general per-pixel kernel, which colour frames always use."""
+    if kernel == "scalar":
+        if C == 3:
+            pytest.skip("colour frames always run the general kernel")
+        monkeypatch.setenv("GOFPID_KNN_SCALAR", "1")
     seed = 12345
     hp = _hot(_shape(H, W, C), blur=None, detector="KNN", morph=(), find_blobs=False, knn_seed=seed)
     ora = cport.KNN(H, W, C, seed)
