@@ -110,7 +110,7 @@ typedef struct gofpid_config {
     double blob_area_min;  /* keep contours with cv.contourArea >= this */
     int32_t max_blobs;     /* capacity: connected components per frame  */
     int32_t max_kept;      /* capacity: blobs that pass the area filter */
-    int32_t max_points;    /* capacity: contour points per frame        */
+    int32_t max_points;    /* capacity: contour points per frame (0: 32 (H + W), within 64 Ki .. 1 Mi) */
 
     /* colour conversion before the blur: pipeline.py:458-459.  Frames have 3 interleaved channels,
      * the path works on their gray value (cv.cvtColor's 15-bit fixed point), computed while the

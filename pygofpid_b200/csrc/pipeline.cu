@@ -686,7 +686,7 @@ GOFPID_API void gofpid_config_default(gofpid_config *cfg)
     cfg->blob_area_min = 100.0; // pipeline.py:555
     cfg->max_blobs = 1 << 16;
     cfg->max_kept = 4096;
-    cfg->max_points = 1 << 20;
+    cfg->max_points = 0; // 0: sized from the frame (see gofpid_pipeline_create)
 }
 
 GOFPID_API int gofpid_gaussian_taps_q8(int n, double sigma, uint16_t *h_taps)
@@ -727,6 +727,10 @@ GOFPID_API int gofpid_pipeline_create(const gofpid_config *cfg, int H, int W, in
     gofpid_pipeline *p = new (std::nothrow) gofpid_pipeline();
     if (!p) { set_error("out of host memory"); return GOFPID_ERR_NOMEM; }
     p->cfg = *cfg;
+    if (p->cfg.max_points <= 0) { // contour points per frame: 32 frame perimeters' worth, 64 Ki .. 1 Mi
+        const long want = 32L * (H + W);
+        p->cfg.max_points = (int)(want < 65536 ? 65536 : (want > (1L << 20) ? (1L << 20) : want));
+    }
     p->H = H; p->W = W; p->C = C; p->Csrc = C; p->n_streams = n_streams; p->device = device;
     if (cfg->convert != GOFPID_CONVERT_NONE) {
         if ((cfg->convert != GOFPID_CONVERT_BGR2GRAY && cfg->convert != GOFPID_CONVERT_RGB2GRAY) || C != 3) {

@@ -58,7 +58,7 @@ class HotPath:
 
     def __init__(self, shape, blur=("gaussian", (3, 3), 4.0), detector="MOG2", morph=(),
                  area_min=100.0, n_streams=1, device=0, find_blobs=True, fd_threshold=5,
-                 knn_seed=0, max_blobs=1 << 16, max_kept=4096, max_points=1 << 20,
+                 knn_seed=0, max_blobs=1 << 16, max_kept=4096, max_points=0,
                  detect_shadows=True, convert=None):
         """convert: None | 'bgr2gray' | 'rgb2gray' -- frames are (H, W, 3) and the path works on their
         gray value (cv.cvtColor of pipeline.py:458-459, computed while the frame is loaded)."""
