@@ -387,7 +387,7 @@ def main():
                          "step": float(np.mean(step_ms))},
             "clocks": clocks,
         }
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:  # (reported at N = 1 only: it takes the host cores ~20 s)
             r = cpu_reference_run(wl, 10, 2, 8)
             line["cpu_baseline"] = {
                 "value": r["fps"], "unit": "frames/s", "cores": r["threads"], "kind": "port",
