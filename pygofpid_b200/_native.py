@@ -9,7 +9,8 @@ import os
 import subprocess
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libgofpid_b200.so")
+# (GOFPID_LIB: file name of a variant build next to the default library -- kernel experiments only)
+LIB_PATH = os.path.join(_HERE, os.environ.get("GOFPID_LIB") or "libgofpid_b200.so")
 CSRC = os.path.join(_HERE, "csrc")
 
 OK = 0

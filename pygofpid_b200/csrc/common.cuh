@@ -109,7 +109,10 @@ struct Mog2Params {
 // MOG2 model, tiled: per stream tiles_x * tiles_y tiles of MOG2_TILE_W x MOG2_TILE_H pixels; a
 // tile is one contiguous block [mode][plane: weight, var, mean c..][512 px] of floats, so its
 // live modes are a single run of bytes for the bulk-copy engine.
-constexpr int MOG2_TILE_W = 64;
+#ifndef GOFPID_MOG2_TILE_W
+#define GOFPID_MOG2_TILE_W 64
+#endif
+constexpr int MOG2_TILE_W = GOFPID_MOG2_TILE_W;
 constexpr int MOG2_TILE_H = 8;
 struct Mog2Model {
     float *planes;      // [stream][tile][5][2 + C][512]

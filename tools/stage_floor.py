@@ -3,9 +3,6 @@ import os, sys, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
-from pygofpid_b200 import _native as nat
-if os.environ.get("GOFPID_LIB"):
-    nat.LIB_PATH = os.path.join(os.path.dirname(nat.LIB_PATH), os.environ["GOFPID_LIB"])
 from pygofpid_b200 import HotPath
 from bench import WORKLOADS, morph_list, make_clip
 wl = WORKLOADS["1080p_mog2_open_close_blobs"]
