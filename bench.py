@@ -3,8 +3,7 @@
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload NAME]
 
-A "step" is one batch of FRAMES_PER_STEP consecutive frames of one camera stream (per GPU)
-through the whole hot path: Gaussian blur -> MOG2 -> open/close -> connected-component blobs
+A "step" is one pass over a 72-frame clip of one camera stream (per GPU) through the whole hot path: Gaussian blur -> MOG2 -> open/close -> connected-component blobs
 (BASELINE.json configs[1], the configuration the metric is quoted on).  N > 1 is launched by
 torchrun, one rank per GPU, each rank owning its own independent stream(s) (weak scaling, no
 data-path collective; torch.distributed is used for the barrier and the max-over-ranks only).
@@ -28,8 +27,9 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-FRAMES_PER_STEP = 32
 CLIP_FRAMES = 72  # distinct frames cycled per stream: 72 x 2.07 MB = 149 MB > 126 MB of L2
+# a step = one pass over the device-resident clip (72 time steps of every stream at 1 stream / GPU)
+# through the clip entry point gofpid_pipeline_process_device_sequence
 
 
 def rect(n):
@@ -92,7 +92,7 @@ class ClockSampler:
         try:
             self.proc = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", "20"],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -202,7 +202,7 @@ def traffic_per_launch(name):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default=DEFAULT_WORKLOAD, choices=sorted(WORKLOADS))
@@ -231,11 +231,11 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     H, W, C, S = wl["H"], wl["W"], wl["C"], args.streams
-    F = FRAMES_PER_STEP
     hp = HotPath((H, W) if C == 1 else (H, W, C), blur=("gaussian", (3, 3), 4.0), detector=wl["detector"],
                  morph=morph_list(wl["morph"]), area_min=100.0, n_streams=S, device=local, knn_seed=12345)
     # synthetic clip: every rank / stream gets its own seed (independent cameras)
     n_clip = CLIP_FRAMES if S == 1 else max(8, CLIP_FRAMES // S)
+    F = n_clip  # frames (time steps) per step
     host = np.stack([make_clip(wl, n_clip, stream=rank * S + s) for s in range(S)], axis=1)  # (T, S, H, W[,C])
     pinned = torch.from_numpy(host).pin_memory()
     dev = pinned.cuda(non_blocking=False)
@@ -245,9 +245,9 @@ def main():
     sh = stream.cuda_stream
 
     def device_step(t0):
-        for i in range(F):
-            t = (t0 + i) % n_clip
-            hp.process_device(dev[t].data_ptr(), row, frame_bytes, sh)
+        # the whole clip, already in HBM, through the clip entry point (MOG2: hp.group frames per
+        # detector launch); per-frame results land in pinned host memory as part of every step
+        hp.enqueue_device_sequence(dev.data_ptr(), n_clip, S * frame_bytes, row, frame_bytes, sh)
 
     def barrier():
         torch.cuda.synchronize()
@@ -268,19 +268,20 @@ def main():
     # ---- timed: device-resident frames ----------------------------------------------------
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = hp.launch_total()
     e0.record(stream)
     for _ in range(args.steps):
         device_step(t_idx); t_idx += F
     e1.record(stream)
     barrier()
     dev_ms = e0.elapsed_time(e1)
-    launches = hp.launch_count() * F * args.steps
+    launches = hp.launch_total() - l0
     info = hp.frame_info()
 
     # ---- timed: end to end through the host entry points (pinned frames in, blob lists out) ----
     # Every frame is copied host->device inside the timed region and its blob list is read back
-    # to the host; frames t+1 .. t+3 are submitted before frame t's results are collected (four
-    # frames in flight, the library's pipelined host API: submit_host / select / blobs).
+    # to the host; frames are submitted ahead of the one whose results are collected (hp.depth frames in
+    # flight, the library's pipelined host API: submit_host / select / blobs).
     e2e_frames = F * max(1, args.steps // 4)
     for i in range(4):  # untimed: first use of the host path allocates its staging buffers
         hp.process_pinned(pinned[(t_idx + i) % n_clip].data_ptr(), row, frame_bytes)
@@ -306,23 +307,30 @@ def main():
 
     # ---- the same end-to-end work through the clip entry point (one library call for a whole
     # clip in pinned host memory: gofpid_pipeline_process_host_sequence) -------------------------
-    seq_frames = min(n_clip, e2e_frames)
-    seq_fps = None
+    seq_calls = max(1, e2e_frames // n_clip)
+    seq_frames = seq_calls * n_clip
+    seq_fps, seq_s, seq_d2h = None, None, 0
     if n_clip >= 8:
         hp.process_sequence(pinned[:8])  # untimed: sizes the output buffers
         barrier()
         w0 = time.perf_counter()
-        counts, _, _ = hp.process_sequence(pinned[:seq_frames])
+        for _ in range(seq_calls):
+            counts, recs, pts = hp.process_sequence(pinned)
+            seq_d2h += 32 * n_clip * S + len(recs) * 56 + pts.shape[0] * 8
         torch.cuda.synchronize()
         seq_s = time.perf_counter() - w0
         seq_fps = seq_frames * S / seq_s
     clocks = sampler.stop() if rank == 0 else None
 
     # ---- per-kernel time of the dominant kernel (CUDA events around it, same steps) --------
+    # one detector launch = G consecutive frames of every stream (G = hp.group; 1 unless MOG2); the
+    # stages run on one stream here, so the events bracket the launch alone
     hp.set_profiling(True)
+    G = hp.group
     det_ms, morph_ms, blob_ms, step_ms = [], [], [], []
-    for i in range(2 * F):
-        hp.process_device(dev[(t_idx + i) % n_clip].data_ptr(), row, frame_bytes, sh)
+    for i in range(max(8, 64 // G)):
+        t0 = (i * G) % (n_clip - G + 1)
+        hp.enqueue_device_sequence(dev[t0].data_ptr(), G, S * frame_bytes, row, frame_bytes, sh)
         st = hp.stage_ms()
         det_ms.append(st["detect"]); morph_ms.append(st["morph"]); blob_ms.append(st["blobs"])
         step_ms.append(st["step"])
@@ -331,9 +339,11 @@ def main():
 
     # ---- aggregate over ranks ---------------------------------------------------------------
     if dist is not None:
-        tt = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device="cuda")
+        tt = torch.tensor([dev_ms, e2e_s, seq_s or 0.0], dtype=torch.float64, device="cuda")
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         dev_ms, e2e_s = float(tt[0]), float(tt[1])
+        if seq_s:
+            seq_fps = seq_frames * S / float(tt[2])
     frames_total = args.steps * F * S * world
     fps = frames_total / (dev_ms * 1e-3)
     e2e_fps = e2e_frames * S * world / e2e_s
@@ -353,7 +363,25 @@ def main():
             nbar = None
             bpp = 3 * C + 1
             kname = "fd_kernel"
-        alg_bytes = bpp * H * W * S
+        per_frame = {"value": e2e_fps, "unit": "frames/s", "frames": e2e_frames,
+                     "api": "gofpid_pipeline_submit_host + gofpid_pipeline_select + gofpid_pipeline_blobs, one call "
+                            "per frame (pinned host frames in, blob lists with contours out, %d frames in flight)" % hp.depth}
+        clip = None if seq_fps is None else {
+            "value": seq_fps * world, "unit": "frames/s", "frames": seq_frames,
+            "api": "gofpid_pipeline_process_host_sequence, one call per 72-frame clip (pinned host frames in, "
+                   "blob lists with contours of every frame out)"}
+        # headline: the faster of the two public host entry points (both copy every frame host->device
+        # and every blob list device->host inside the timed region); the other one is reported beside it
+        use_clip = clip is not None and clip["value"] >= e2e_fps
+        e2e_obj = {"value": clip["value"] if use_clip else e2e_fps, "unit": "frames/s",
+                   "h2d_bytes_per_step": frame_bytes * S * F,
+                   "d2h_bytes_per_step": int((seq_d2h / max(seq_frames, 1) if use_clip else d2h / max(e2e_frames, 1)) * F),
+                   "frames": seq_frames if use_clip else e2e_frames,
+                   "mpix_per_s": (clip["value"] if use_clip else e2e_fps) * mpix,
+                   "blobs_per_frame": nblobs / max(e2e_frames * S, 1),
+                   "api": (clip if use_clip else per_frame)["api"],
+                   "clip_call": clip, "per_frame_call": per_frame}
+        alg_bytes = bpp * H * W * S * G  # one launch: G frames of S streams
         achieved = alg_bytes / (det * 1e-3) / 1e9
         line = {
             "metric": "frames_per_sec", "value": fps, "unit": "frames/s", "n_gpus": world,
@@ -363,28 +391,23 @@ def main():
             "mpix_per_s": fps * mpix, "frames_per_sec_per_gpu": fps / world,
             "config": {"workload": args.workload, "frames_per_step": F, "streams_per_gpu": S,
                        "shape": [H, W, C], "clip_frames": n_clip,
-                       "l2": "inputs cycle through a %.0f MB clip (> 126 MB L2); the MOG2 model is resident in HBM"
+                       "l2": "inputs cycle through a %.0f MB clip (> 126 MB L2); the background model is resident in HBM"
                              % (n_clip * S * frame_bytes / 1e6),
+                       "api": "gofpid_pipeline_process_device_sequence (clip in HBM, %d frames per detector launch, "
+                              "%d frame slots)" % (hp.group, hp.depth),
                        "blobs_last_frame": info["n_kept"], "components_last_frame": info["n_components"]},
-            "e2e": {"value": e2e_fps, "unit": "frames/s", "h2d_bytes_per_step": frame_bytes * S * F,
-                    "d2h_bytes_per_step": int(d2h / max(e2e_frames, 1) * F), "frames": e2e_frames,
-                    "mpix_per_s": e2e_fps * mpix,
-                    "blobs_per_frame": nblobs / max(e2e_frames * S, 1),
-                    "clip_call": None if seq_fps is None else {
-                        "value": seq_fps * world, "unit": "frames/s", "frames": seq_frames,
-                        "api": "gofpid_pipeline_process_host_sequence (one call per clip of pinned host frames, "
-                               "blob lists of every frame out)"},
-                    "api": "gofpid_pipeline_submit_host + gofpid_pipeline_select + gofpid_pipeline_blobs "
-                           "(pinned host frames in, blob lists with contours out, %d frames in flight)" % hp.depth},
+            "e2e": e2e_obj,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic_per_launch(kname),
                          "peak_source": peak_src, "kernel_ms": det, "algorithmic_bytes": alg_bytes,
-                         "bytes_per_pixel": bpp, "mean_modes": nbar,
+                         "bytes_per_pixel": bpp, "mean_modes": nbar, "frames_per_launch": G,
+                         "kernel_us_per_frame": det * 1e3 / G,
                          "how": "CUDA events around the kernel on the launch stream, mean of %d launches" % len(det_ms),
                          "frac_of_nominal_8TBs": achieved / 8000.0},
-            "stage_ms": {"detect": det, "morph": float(np.mean(morph_ms)), "blobs": float(np.mean(blob_ms)),
-                         "step": float(np.mean(step_ms))},
+            "stage_ms": {"detect_launch": det, "morph_first_frame": float(np.mean(morph_ms)),
+                         "rest_of_group": float(np.mean(blob_ms)), "group": float(np.mean(step_ms)),
+                         "frames_per_group": G},
             "clocks": clocks,
         }
         if not args.no_cpu_baseline and world == 1:  # (reported at N = 1 only: it takes the host cores ~20 s)

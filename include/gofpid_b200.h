@@ -187,6 +187,21 @@ GOFPID_API int gofpid_pipeline_process_host_sequence(gofpid_pipeline *p, const u
                                                      int blob_capacity, int32_t *h_points,
                                                      int point_capacity, int32_t *h_counts);
 
+/* The same for a clip that already is in device memory (frame t at d_frames + t * frame_stride);
+ * the detector launches are enqueued on `stream`.  With h_counts == NULL nothing is collected: the
+ * call only enqueues the work and the newest `depth` frames stay selectable (gofpid_pipeline_select).
+ * Both clip entry points carry MOG2 through gofpid_pipeline_group() consecutive frames per detector
+ * launch (a tile's modes stay in shared memory meanwhile: the model is read and written once per
+ * group); results are identical to frame-by-frame calls. */
+GOFPID_API int gofpid_pipeline_process_device_sequence(gofpid_pipeline *p, const uint8_t *d_frames,
+                                                       int n_frames, size_t frame_stride, size_t pitch,
+                                                       size_t stream_stride, void *stream,
+                                                       gofpid_blob *h_blobs, int blob_capacity,
+                                                       int32_t *h_points, int point_capacity,
+                                                       int32_t *h_counts);
+/* Frames per detector launch in the clip entry points (1 unless the detector is MOG2). */
+GOFPID_API int gofpid_pipeline_group(gofpid_pipeline *p);
+
 /* Asynchronous variant of process_host for pinned host frames: enqueues the host->device copy
  * and the step and returns; several frames are in flight (morphology / labelling / tracing of
  * frames t, t-1, ... overlap the model update of frame t+1).  Results are collected later with
@@ -194,7 +209,7 @@ GOFPID_API int gofpid_pipeline_process_host_sequence(gofpid_pipeline *p, const u
 GOFPID_API int gofpid_pipeline_submit_host(gofpid_pipeline *p, const uint8_t *h_frames,
                                            size_t pitch, size_t stream_stride);
 /* Which frame the result getters refer to: age 0 = newest submitted frame (default after every
- * process/submit call), 1 = the one before it, ... up to the pipeline depth - 1 (3). */
+ * process/submit call), 1 = the one before it, ... up to gofpid_pipeline_depth() - 1. */
 GOFPID_API int gofpid_pipeline_select(gofpid_pipeline *p, int age);
 /* Frame slots of the handle = frames that can be in flight (submit_host) at once. */
 GOFPID_API int gofpid_pipeline_depth(gofpid_pipeline *p);
@@ -237,11 +252,15 @@ GOFPID_API int gofpid_pipeline_mog2_mean_modes(gofpid_pipeline *p, double *mean_
 /* Timing aid for bench.py: device time (ms, CUDA events on the pipeline's launch stream)
  * spent in each stage kernel group during the last process call:
  * [0] fused blur+detect kernel(s), [1] morphology, [2] labelling+stats+contours,
- * [3] frame tick, [4] whole step. */
+ * [3] frame tick, [4] whole step.  After a clip call that grouped frames (MOG2): [0] the group's
+ * ONE detector launch (gofpid_pipeline_group() frames), [1] morphology of the group's first frame,
+ * [2] the rest of the group's stage B, [4] the whole group. */
 GOFPID_API int gofpid_pipeline_set_profiling(gofpid_pipeline *p, int enabled);
 GOFPID_API int gofpid_pipeline_stage_ms(gofpid_pipeline *p, float *h_ms5);
 /* Number of kernels the last process call launched. */
 GOFPID_API int gofpid_pipeline_launch_count(gofpid_pipeline *p);
+/* Number of kernels launched since creation / the last reset (all entry points). */
+GOFPID_API int gofpid_pipeline_launch_total(gofpid_pipeline *p, long long *n_launches);
 
 /* ---- stage-level entry points (device buffers, used by the parity tests) ------------- */
 /* cv.GaussianBlur / cv.blur on u8, BORDER_REFLECT_101 (pipeline.py:463). */

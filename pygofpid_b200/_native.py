@@ -87,6 +87,10 @@ SIGNATURES = {
     "gofpid_pipeline_submit_host": (ct.c_int, [_vp, _vp, _sz, _sz]),
     "gofpid_pipeline_process_host_sequence": (ct.c_int, [_vp, _vp, ct.c_int, _sz, _sz, _sz, ct.POINTER(Blob), ct.c_int,
                                                          ct.POINTER(ct.c_int32), ct.c_int, ct.POINTER(ct.c_int32)]),
+    "gofpid_pipeline_process_device_sequence": (ct.c_int, [_vp, _vp, ct.c_int, _sz, _sz, _sz, _vp, ct.POINTER(Blob),
+                                                           ct.c_int, ct.POINTER(ct.c_int32), ct.c_int,
+                                                           ct.POINTER(ct.c_int32)]),
+    "gofpid_pipeline_group": (ct.c_int, [_vp]),
     "gofpid_pipeline_select": (ct.c_int, [_vp, ct.c_int]),
     "gofpid_pipeline_depth": (ct.c_int, [_vp]),
     "gofpid_pipeline_frame_info": (ct.c_int, [_vp, ct.c_int, ct.POINTER(FrameInfo)]),
@@ -103,6 +107,7 @@ SIGNATURES = {
     "gofpid_pipeline_set_profiling": (ct.c_int, [_vp, ct.c_int]),
     "gofpid_pipeline_stage_ms": (ct.c_int, [_vp, _f32p]),
     "gofpid_pipeline_launch_count": (ct.c_int, [_vp]),
+    "gofpid_pipeline_launch_total": (ct.c_int, [_vp, ct.POINTER(ct.c_longlong)]),
     "gofpid_blur_u8": (ct.c_int, [_vp, _sz, _vp, _sz, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int,
                                   ct.c_int, ct.c_double, _vp]),
     "gofpid_morph_u8": (ct.c_int, [_vp, _sz, _vp, _sz, ct.c_int, ct.c_int, ct.POINTER(MorphOp), ct.c_int,

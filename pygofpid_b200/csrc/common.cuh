@@ -82,8 +82,9 @@ struct ImageU8 {
 // CUDA graph can be replayed unchanged.
 struct FrameTick {
     int32_t nframes;  // 1-based index of the frame being processed
-    // MOG2
-    float alphaT, alpha1, prune;
+    // MOG2: alphaT, alpha1, prune of the next MOG2_MAX_GROUP frames (a launch consumes the first
+    // `nf` of them, its last tile prepares the following ones)
+    alignas(16) float mog2_lr[8][4];
     // KNN
     int32_t knn_u[3];       // update periods uS, uM, uL
     int32_t knn_counter[3]; // counters cS, cM, cL valid DURING the frame
@@ -114,6 +115,14 @@ struct Mog2Params {
 #endif
 constexpr int MOG2_TILE_W = GOFPID_MOG2_TILE_W;
 constexpr int MOG2_TILE_H = 8;
+// Temporal blocking: one launch carries a tile through up to MOG2_MAX_GROUP consecutive frames of
+// its stream while the tile's modes stay in shared memory (model read and written once per group).
+constexpr int MOG2_MAX_GROUP = 8;
+struct Mog2Group {
+    const uint8_t *frame[MOG2_MAX_GROUP]; // frame f of the group (stream 0; FrameSrc::pitch / stream_stride apply)
+    uint8_t *mask[MOG2_MAX_GROUP];        // detector mask of frame f (stream 0; ImageU8::pitch / stream_stride apply)
+    int nf;                               // frames in this launch (1 .. MOG2_MAX_GROUP)
+};
 struct Mog2Model {
     float *planes;      // [stream][tile][5][2 + C][512]
     uint8_t *nmodes;    // [stream][tile][512]
@@ -166,16 +175,20 @@ int launch_fd(const DetectLaunch &L, FdModel model, int thr);
 // pipeline so that a captured step can be replayed with a new frame pointer
 struct Mog2Args {
     BlurParams bp;
-    ImageU8 mask;
+    ImageU8 mask;   // pitch / stream stride of the masks (bases: grp.mask)
     Mog2Model M;
     Mog2Params P;
     FrameTick *tick;
-    FrameSrc src;
+    FrameSrc src;   // pitch / stream stride of the frames (bases: grp.frame)
+    Mog2Group grp;
     int H, W;
 };
-int launch_mog2(const DetectLaunch &L, Mog2Model model, const Mog2Params &mp, FrameTick *tick);
+// one frame (L.src / L.mask) when grp == nullptr, else the frames and masks of the group
+int launch_mog2(const DetectLaunch &L, Mog2Model model, const Mog2Params &mp, FrameTick *tick,
+                const Mog2Group *grp = nullptr);
+void mog2_prepare_lr(const Mog2Params &mp, long n_done, float (*lr)[4]); // rates of frames n_done+1 ..
 const void *mog2_kernel_func(int C);
-void mog2_kernel_params(Mog2Args &a, void **params); // params[8]
+void mog2_kernel_params(Mog2Args &a, void **params); // params[9]
 int launch_knn(const DetectLaunch &L, KnnModel model, const KnnParams &kp,
                const uint64_t *d_jump_table);
 int detect_launches_per_step(int detector);

@@ -36,9 +36,14 @@ using namespace gofpid;
 // sequential; stage B only needs the finished mask of its own frame and occupies a handful of
 // SMs (one CTA per stream or per blob), so consecutive frames of ONE camera stream overlap and
 // the frame rate is set by stage A alone.
-constexpr int MAX_DEPTH = 8;
+constexpr int MAX_DEPTH = 16;
 constexpr int DEFAULT_DEPTH = 6;       // few camera streams per handle: deep, stage B latency is several stage As
 constexpr int DEFAULT_DEPTH_MANY = 4;  // many streams per handle: every kernel is already wide, slots cost memory
+// MOG2 handles: the clip entry points carry a tile through DEFAULT_GROUP consecutive frames per
+// launch (temporal blocking, see mog2_kernel), which wants two groups' worth of slots and a few more
+constexpr int DEFAULT_GROUP = 3; // (measured: 2 / 3 / 4 / 8 frames per launch = 30.7 / 28.2 / 33.8 / 32.0 us per 1080p frame with blobs)
+constexpr int DEFAULT_DEPTH_MOG2 = 12, DEFAULT_DEPTH_MOG2_MANY = 8;
+// (GOFPID_MOG2_GROUP overrides: 1 .. MOG2_MAX_GROUP, at most half the slots)
 // (GOFPID_DEPTH overrides: 1 .. MAX_DEPTH)
 
 struct FrameSlot {
@@ -70,6 +75,9 @@ struct gofpid_pipeline {
     cudaStream_t stream = nullptr;   // own stage-A stream (host entry points)
     cudaStream_t stream_b[MAX_DEPTH] = {}; // stage B, one per frame slot
     int depth = DEFAULT_DEPTH;            // frame slots in use
+    int group = 1;                        // frames per MOG2 launch in the clip entry points
+    int launches_b = 0;                   // kernels of one captured stage B
+    long long launches_total = 0;         // kernels launched since creation / reset
     int prefix_kept = 0, prefix_points = 0; // blob records / contour points copied to the host with every step
     cudaStream_t stream_c = nullptr; // result fetches
     cudaStream_t stream_h = nullptr; // host->device frame copies
@@ -175,11 +183,8 @@ int reset_state(gofpid_pipeline *p)
     FrameTick t;
     memset(&t, 0, sizeof(t));
     t.knn_rng = p->cfg.knn_rng_seed ? p->cfg.knn_rng_seed : 0xffffffffULL;
-    if (p->cfg.detector == GOFPID_DETECT_MOG2) { // learning rate of frame 1 (mog2_kernel prepares the following ones)
-        const long n2 = 2;
-        const double lr = 1.0 / (double)(n2 < p->mog2p.history ? n2 : p->mog2p.history);
-        t.alphaT = (float)lr; t.alpha1 = 1.0f - (float)lr; t.prune = (float)(-lr * (double)p->mog2p.ct);
-    }
+    if (p->cfg.detector == GOFPID_DETECT_MOG2) // learning rates of the first frames (mog2_kernel prepares the following ones)
+        mog2_prepare_lr(p->mog2p, 0, t.mog2_lr);
     GOFPID_CUDA_TRY(cudaMemcpy(p->d_tick, &t, sizeof(t), cudaMemcpyHostToDevice));
     if (p->cfg.detector == GOFPID_DETECT_MOG2) {
         const size_t nt = (size_t)p->mog2.tiles_x * p->mog2.tiles_y * p->n_streams;
@@ -194,6 +199,7 @@ int reset_state(gofpid_pipeline *p)
     for (auto &S : p->slots) { S.used = false; S.fetched = false; S.frame_index = 0; }
     p->frames = 0;
     p->selected = 0;
+    p->launches_total = 0;
     return GOFPID_OK;
 }
 
@@ -238,9 +244,15 @@ int build(gofpid_pipeline *p)
     for (cudaStream_t *s : {&p->stream, &p->stream_c, &p->stream_h})
         GOFPID_CUDA_TRY(cudaStreamCreateWithFlags(s, cudaStreamNonBlocking));
     {
-        p->depth = p->n_streams <= 8 ? DEFAULT_DEPTH : DEFAULT_DEPTH_MANY;
+        const bool mog2 = cfg.detector == GOFPID_DETECT_MOG2;
+        if (mog2) p->depth = p->n_streams <= 8 ? DEFAULT_DEPTH_MOG2 : DEFAULT_DEPTH_MOG2_MANY;
+        else p->depth = p->n_streams <= 8 ? DEFAULT_DEPTH : DEFAULT_DEPTH_MANY;
         const char *e = getenv("GOFPID_DEPTH");
         if (e && atoi(e) >= 1 && atoi(e) <= MAX_DEPTH) p->depth = atoi(e);
+        p->group = mog2 ? DEFAULT_GROUP : 1;
+        const char *ge = getenv("GOFPID_MOG2_GROUP");
+        if (mog2 && ge && atoi(ge) >= 1 && atoi(ge) <= MOG2_MAX_GROUP) p->group = atoi(ge);
+        p->group = std::max(1, std::min(p->group, p->depth / 2));
         // stage B runs at a higher priority than stage A: its few CTAs take the SMs they need as soon
         // as the detector's CTAs drain instead of queueing behind the whole grid
         int lo = 0, hi = 0;
@@ -354,8 +366,10 @@ int build(gofpid_pipeline *p)
         FrameSlot &F = p->slots[si];
         GOFPID_TRY(alloc_zero((void **)&F.d_final, p->mask_stream * S));
         if (cfg.n_morph > 0) GOFPID_TRY(alloc_zero((void **)&F.d_mask_det, p->mask_stream * S));
-        GOFPID_CUDA_TRY(cudaEventCreateWithFlags(&F.ev_mask, cudaEventDisableTiming));
-        GOFPID_CUDA_TRY(cudaEventCreateWithFlags(&F.ev_blobs, cudaEventDisableTiming));
+        const char *et = getenv("GOFPID_EVENT_TIMING"); // (tools/timeline_debug.py: when does each slot's stage end)
+        const unsigned evf = (et && et[0] == '1') ? cudaEventDefault : cudaEventDisableTiming;
+        GOFPID_CUDA_TRY(cudaEventCreateWithFlags(&F.ev_mask, evf));
+        GOFPID_CUDA_TRY(cudaEventCreateWithFlags(&F.ev_blobs, evf));
         GOFPID_CUDA_TRY(cudaEventCreateWithFlags(&F.ev_h2d, cudaEventDisableTiming));
         GOFPID_CUDA_TRY(cudaMallocHost(&F.h_info, sizeof(gofpid_frame_info) * S));
         memset(F.h_info, 0, sizeof(gofpid_frame_info) * S);
@@ -405,7 +419,10 @@ int enqueue_stage_a(gofpid_pipeline *p, FrameSlot &F, const FrameSrc &src, cudaS
     L.stream = s;
     if (mog2) {
         GOFPID_TRY(launch_mog2(L, p->mog2, p->mog2p, p->d_tick));
-        F.mog2_args = Mog2Args{L.blur, L.mask, p->mog2, p->mog2p, p->d_tick, src, p->H, p->W};
+        Mog2Group one;
+        memset(&one, 0, sizeof(one));
+        one.frame[0] = src.base; one.mask[0] = L.mask.base; one.nf = 1;
+        F.mog2_args = Mog2Args{L.blur, L.mask, p->mog2, p->mog2p, p->d_tick, src, one, p->H, p->W};
     }
     else if (p->cfg.detector == GOFPID_DETECT_KNN) GOFPID_TRY(launch_knn(L, p->knn, p->knnp, p->d_pow2tab));
     else GOFPID_TRY(launch_fd(L, p->fd, p->fd_thr));
@@ -493,6 +510,7 @@ int build_graphs(gofpid_pipeline *p, FrameSlot &F, const FrameSrc &src)
         GOFPID_CUDA_TRY(cudaGraphInstantiate(&F.exec_b, F.graph_b, 0));
     }
     p->graph_launches = la + lb;
+    p->launches_b = lb;
     return GOFPID_OK;
 }
 
@@ -520,6 +538,7 @@ int run_step(gofpid_pipeline *p, const uint8_t *d_frames, size_t pitch, size_t s
             void *params[10];
             if (p->cfg.detector == GOFPID_DETECT_MOG2) {
                 F.mog2_args.src = src;
+                F.mog2_args.grp.frame[0] = src.base;
                 mog2_kernel_params(F.mog2_args, params);
             } else {
                 p->tick_args.src = src;
@@ -545,9 +564,88 @@ int run_step(gofpid_pipeline *p, const uint8_t *d_frames, size_t pitch, size_t s
         }
     }
     p->launch_count = la + lb;
+    p->launches_total += la + lb;
     F.used = true;
     F.fetched = false;
     F.frame_index = (int)(++p->frames);
+    p->selected = 0;
+    return GOFPID_OK;
+}
+
+// g consecutive time steps (MOG2) through ONE stage-A launch: the fused kernel keeps every tile's modes
+// in shared memory while it walks the tile through the g frames, so the model is read and written once
+// per group instead of once per frame and the launch / ramp / tail of the grid is paid once.  The g
+// stage Bs then start together, each on its slot's stream.  frames[f]: frame f of stream 0.
+int run_group(gofpid_pipeline *p, const uint8_t *const *frames, int g, size_t pitch, size_t stream_stride,
+              cudaStream_t s)
+{
+    if (g == 1 || p->cfg.detector != GOFPID_DETECT_MOG2 || !p->use_graph || p->frames < p->depth ||
+        g > p->depth || g > MOG2_MAX_GROUP) {
+        for (int f = 0; f < g; f++) GOFPID_TRY(run_step(p, frames[f], pitch, stream_stride, s));
+        return GOFPID_OK;
+    }
+    const bool stage_b = p->cfg.find_blobs || p->cfg.n_morph > 0;
+    Mog2Group grp;
+    memset(&grp, 0, sizeof(grp));
+    grp.nf = g;
+    FrameSlot *slot[MOG2_MAX_GROUP];
+    for (int f = 0; f < g; f++) {
+        FrameSlot &F = p->slots[(p->frames + f) % p->depth];
+        slot[f] = &F;
+        // the slot's previous frame must be done with its masks before they are overwritten
+        if (F.used) GOFPID_CUDA_TRY(cudaStreamWaitEvent(s, F.ev_blobs, 0));
+        if (!F.exec_a) GOFPID_TRY(build_graphs(p, F, FrameSrc{frames[f], pitch, stream_stride}));
+        grp.frame[f] = frames[f];
+        grp.mask[f] = p->cfg.n_morph > 0 ? F.d_mask_det : F.d_final;
+    }
+    DetectLaunch L;
+    L.H = p->H; L.W = p->W; L.C = p->C; L.n_streams = p->n_streams;
+    L.src = FrameSrc{frames[0], pitch, stream_stride};
+    L.blur = p->blur;
+    L.mask = ImageU8{grp.mask[0], p->mask_pitch, p->mask_stream};
+    L.tick = p->d_tick;
+    L.stream = s;
+    if (p->profiling) { // everything on one stream, events around the group's detector launch
+        GOFPID_CUDA_TRY(cudaEventRecord(p->ev[0], s));
+        GOFPID_CUDA_TRY(cudaEventRecord(p->ev[4], s));
+        GOFPID_TRY(launch_mog2(L, p->mog2, p->mog2p, p->d_tick, &grp));
+        GOFPID_CUDA_TRY(cudaEventRecord(p->ev[1], s));
+        int lb = 0;
+        for (int f = 0; f < g; f++) {
+            FrameSlot &F = *slot[f];
+            if (stage_b) GOFPID_TRY(enqueue_stage_b(p, F, s, f == 0, &lb));
+            else if (f == 0) GOFPID_CUDA_TRY(cudaEventRecord(p->ev[2], s));
+            GOFPID_CUDA_TRY(cudaEventRecord(F.ev_mask, s));
+            GOFPID_CUDA_TRY(cudaEventRecord(F.ev_blobs, s));
+            F.used = true;
+            F.fetched = false;
+            F.frame_index = (int)(++p->frames);
+        }
+        GOFPID_CUDA_TRY(cudaEventRecord(p->ev[3], s));
+        p->launch_count = 1 + lb;
+        p->launches_total += 1 + (long long)g * lb;
+        p->selected = 0;
+        return GOFPID_OK;
+    }
+    GOFPID_TRY(launch_mog2(L, p->mog2, p->mog2p, p->d_tick, &grp));
+    GOFPID_CUDA_TRY(cudaEventRecord(slot[0]->ev_mask, s));
+    for (int f = 0; f < g; f++) {
+        FrameSlot &F = *slot[f];
+        if (f > 0) GOFPID_CUDA_TRY(cudaEventRecord(F.ev_mask, s)); // (same point of the stream: every slot has its own event)
+        if (stage_b) {
+            cudaStream_t sb = p->stream_b[&F - p->slots];
+            GOFPID_CUDA_TRY(cudaStreamWaitEvent(sb, slot[0]->ev_mask, 0));
+            GOFPID_CUDA_TRY(cudaGraphLaunch(F.exec_b, sb));
+            GOFPID_CUDA_TRY(cudaEventRecord(F.ev_blobs, sb));
+        } else {
+            GOFPID_CUDA_TRY(cudaEventRecord(F.ev_blobs, s));
+        }
+        F.used = true;
+        F.fetched = false;
+        F.frame_index = (int)(++p->frames);
+    }
+    p->launch_count = 1 + p->launches_b; // (kernels of the newest frame: its share of the group launch + stage B)
+    p->launches_total += 1 + (long long)g * p->launches_b;
     p->selected = 0;
     return GOFPID_OK;
 }
@@ -590,12 +688,13 @@ int fetch_results(gofpid_pipeline *p, FrameSlot *F)
     return GOFPID_OK;
 }
 
-// Host frames -> the slot's staging buffer (asynchronous when the source is pinned), then the step.
-int submit_host(gofpid_pipeline *p, const uint8_t *h_frames, size_t pitch, size_t stream_stride)
+// Host frames -> the staging buffer of the slot `ahead` steps after the next one (asynchronous when
+// the source is pinned).
+int stage_host_frames(gofpid_pipeline *p, int ahead, const uint8_t *h_frames, size_t pitch, size_t stream_stride)
 {
     const size_t row = (size_t)p->W * p->Csrc;
     if (pitch < row) { set_error("pitch %zu smaller than a row (%zu bytes)", pitch, row); return GOFPID_ERR_INVALID; }
-    FrameSlot &F = p->slots[p->frames % p->depth];
+    FrameSlot &F = p->slots[(p->frames + ahead) % p->depth];
     if (!p->frames_pitch) {
         p->frames_pitch = round_up(row, 128);
         p->frames_stream = p->frames_pitch * p->H;
@@ -637,7 +736,65 @@ int submit_host(gofpid_pipeline *p, const uint8_t *h_frames, size_t pitch, size_
     }
     GOFPID_CUDA_TRY(cudaEventRecord(F.ev_h2d, sh));
     GOFPID_CUDA_TRY(cudaStreamWaitEvent(p->stream, F.ev_h2d, 0));
+    return GOFPID_OK;
+}
+
+// Host frames -> the slot's staging buffer, then the step.
+int submit_host(gofpid_pipeline *p, const uint8_t *h_frames, size_t pitch, size_t stream_stride)
+{
+    GOFPID_TRY(stage_host_frames(p, 0, h_frames, pitch, stream_stride));
+    FrameSlot &F = p->slots[p->frames % p->depth];
     return run_step(p, F.d_frames, p->frames_pitch, p->frames_stream, p->stream);
+}
+
+// A clip, in device or host memory: the pipelined loop (submit frames, collect the frame whose slot
+// is needed next) that a caller of submit / select / blobs would write, without the per-call
+// overhead -- and, for MOG2, with `group` frames per detector launch (run_group).
+int run_sequence(gofpid_pipeline *p, const uint8_t *frames, bool host, int n_frames, size_t frame_stride,
+                 size_t pitch, size_t stream_stride, cudaStream_t s, gofpid_blob *h_blobs, int blob_capacity,
+                 int32_t *h_points, int point_capacity, int32_t *h_counts)
+{
+    const int S = p->n_streams;
+    int nb_total = 0, np_total = 0;
+    int t = 0, c = 0; // frames of this clip submitted / collected
+    auto collect = [&](int upto) -> int { // every frame of the clip up to `upto` (inclusive)
+        for (; c <= upto; c++) {
+            p->selected = t - 1 - c;
+            for (int z = 0; z < S; z++) {
+                int nb = 0, np = 0;
+                const int rc = gofpid_pipeline_blobs(p, z, h_blobs ? h_blobs + nb_total : nullptr, blob_capacity - nb_total,
+                                                     h_points ? h_points + (size_t)np_total * 2 : nullptr,
+                                                     point_capacity - np_total, &nb, &np);
+                if (rc != GOFPID_OK) { p->selected = 0; return rc; }
+                h_counts[((size_t)c * S + z) * 2] = nb;
+                h_counts[((size_t)c * S + z) * 2 + 1] = np;
+                if (h_blobs || h_points) { nb_total += nb; np_total += np; }
+            }
+        }
+        p->selected = 0;
+        return GOFPID_OK;
+    };
+    while (t < n_frames) {
+        int g = 1;
+        if (p->group > 1 && p->frames >= p->depth && p->use_graph) g = std::min(p->group, n_frames - t);
+        // frames t .. t+g-1 take the slots of frames t-depth .. t+g-1-depth: collect those first
+        if (h_counts) GOFPID_TRY(collect(t + g - 1 - p->depth));
+        const uint8_t *ptr[MOG2_MAX_GROUP];
+        for (int f = 0; f < g; f++) {
+            const uint8_t *src = frames + (size_t)(t + f) * frame_stride;
+            if (host) {
+                GOFPID_TRY(stage_host_frames(p, f, src, pitch, stream_stride));
+                ptr[f] = p->slots[(p->frames + f) % p->depth].d_frames;
+            } else {
+                ptr[f] = src;
+            }
+        }
+        if (host) GOFPID_TRY(run_group(p, ptr, g, p->frames_pitch, p->frames_stream, p->stream));
+        else GOFPID_TRY(run_group(p, ptr, g, pitch, stream_stride, s));
+        t += g;
+    }
+    if (h_counts) GOFPID_TRY(collect(n_frames - 1));
+    return GOFPID_OK;
 }
 
 } // namespace
@@ -817,26 +974,59 @@ GOFPID_API int gofpid_pipeline_process_host_sequence(gofpid_pipeline *p, const u
     GOFPID_GUARD(p);
     if (!h_frames || n_frames < 0 || !h_counts) { set_error("bad argument"); return GOFPID_ERR_INVALID; }
     if (!p->cfg.find_blobs) { set_error("pipeline was created with find_blobs = 0"); return GOFPID_ERR_INVALID; }
-    const int lag = p->depth - 1, S = p->n_streams;
-    int nb_total = 0, np_total = 0;
-    for (int t = 0; t < n_frames + lag; t++) {
-        if (t < n_frames) GOFPID_TRY(submit_host(p, h_frames + (size_t)t * frame_stride, pitch, stream_stride));
-        const int c = t - lag; // frame to collect
-        if (c < 0) continue;
-        const int newest = t < n_frames ? t : n_frames - 1;
-        p->selected = newest - c;
-        for (int z = 0; z < S; z++) {
-            int nb = 0, np = 0;
-            const int rc = gofpid_pipeline_blobs(p, z, h_blobs ? h_blobs + nb_total : nullptr, blob_capacity - nb_total,
-                                                 h_points ? h_points + (size_t)np_total * 2 : nullptr,
-                                                 point_capacity - np_total, &nb, &np);
-            if (rc != GOFPID_OK) { p->selected = 0; return rc; }
-            h_counts[((size_t)c * S + z) * 2] = nb;
-            h_counts[((size_t)c * S + z) * 2 + 1] = np;
-            if (h_blobs || h_points) { nb_total += nb; np_total += np; }
-        }
+    return run_sequence(p, h_frames, true, n_frames, frame_stride, pitch, stream_stride, p->stream, h_blobs,
+                        blob_capacity, h_points, point_capacity, h_counts);
+}
+
+// The same for a clip that is already in device memory (frames frame_stride bytes apart); stage A is
+// enqueued on `stream`.  h_counts == NULL: nothing is collected (the newest `depth` frames stay
+// selectable), the call only enqueues work.
+GOFPID_API int gofpid_pipeline_process_device_sequence(gofpid_pipeline *p, const uint8_t *d_frames, int n_frames,
+                                                       size_t frame_stride, size_t pitch, size_t stream_stride,
+                                                       void *stream, gofpid_blob *h_blobs, int blob_capacity,
+                                                       int32_t *h_points, int point_capacity, int32_t *h_counts)
+{
+    GOFPID_GUARD(p);
+    if (!d_frames || n_frames < 0) { set_error("bad argument"); return GOFPID_ERR_INVALID; }
+    if (h_counts && !p->cfg.find_blobs) { set_error("pipeline was created with find_blobs = 0"); return GOFPID_ERR_INVALID; }
+    if (pitch < (size_t)p->W * p->Csrc) { set_error("pitch %zu smaller than a row (%d bytes)", pitch, p->W * p->Csrc); return GOFPID_ERR_INVALID; }
+    return run_sequence(p, d_frames, false, n_frames, frame_stride, pitch, stream_stride, (cudaStream_t)stream, h_blobs,
+                        blob_capacity, h_points, point_capacity, h_counts);
+}
+
+// Debug aids (not part of the ABI in include/): a mark on `stream`, then per slot the milliseconds
+// from the mark to the end of the slot's stage A and stage B (needs GOFPID_EVENT_TIMING=1).
+GOFPID_API int gofpid_debug_mark(gofpid_pipeline *p, void *stream)
+{
+    GOFPID_GUARD(p);
+    GOFPID_CUDA_TRY(cudaEventRecord(p->ev[5], (cudaStream_t)stream));
+    return GOFPID_OK;
+}
+GOFPID_API int gofpid_debug_slot_times(gofpid_pipeline *p, float *ms2, int *frame_index)
+{
+    GOFPID_GUARD(p);
+    GOFPID_CUDA_TRY(cudaDeviceSynchronize());
+    for (int i = 0; i < p->depth; i++) {
+        FrameSlot &F = p->slots[i];
+        ms2[2 * i] = ms2[2 * i + 1] = -1.f;
+        frame_index[i] = F.frame_index;
+        if (!F.used) continue;
+        if (cudaEventElapsedTime(&ms2[2 * i], p->ev[5], F.ev_mask) != cudaSuccess) cudaGetLastError();
+        if (cudaEventElapsedTime(&ms2[2 * i + 1], p->ev[5], F.ev_blobs) != cudaSuccess) cudaGetLastError();
     }
-    p->selected = 0;
+    return GOFPID_OK;
+}
+
+GOFPID_API int gofpid_pipeline_group(gofpid_pipeline *p)
+{
+    return p ? p->group : 0;
+}
+
+GOFPID_API int gofpid_pipeline_launch_total(gofpid_pipeline *p, long long *n_launches)
+{
+    GOFPID_GUARD(p);
+    if (!n_launches) { set_error("null output pointer"); return GOFPID_ERR_INVALID; }
+    *n_launches = p->launches_total;
     return GOFPID_OK;
 }
 

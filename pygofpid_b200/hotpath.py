@@ -232,7 +232,8 @@ class HotPath:
             return recs[:nb.value], (out.copy() if copy else out)
 
     def process_sequence(self, frames, blob_capacity=None, point_capacity=None):
-        """A whole clip from HOST memory in one library call (gofpid_pipeline_process_host_sequence):
+        """A whole clip from HOST memory -- or a CUDA uint8 tensor -- in one library call
+        (gofpid_pipeline_process_host_sequence / gofpid_pipeline_process_device_sequence):
         frames (T, H, W[, C]) for one stream or (T, n_streams, H, W[, C]).  Returns (counts, records,
         points): counts[t, z] = (blobs, points) of frame t / stream z, records a numpy structured
         array (fields of gofpid_blob) and points (n, 2) int32, both in frame order."""
@@ -258,15 +259,35 @@ class HotPath:
         counts = np.zeros((T, self.n_streams, 2), np.int32)
         recs = np.empty(bc, BLOB_DTYPE)
         pts = np.empty((pc, 2), np.int32)
-        rc = self._L.gofpid_pipeline_process_host_sequence(
-            self._h, ptr, T, row * self.H * self.n_streams, row, row * self.H,
-            recs.ctypes.data_as(ct.POINTER(nat.Blob)), bc, pts.ctypes.data_as(ct.POINTER(ct.c_int32)), pc,
-            counts.ctypes.data_as(ct.POINTER(ct.c_int32)))
+        if getattr(frames, "is_cuda", False):  # a clip that already is in device memory
+            import torch
+            rc = self._L.gofpid_pipeline_process_device_sequence(
+                self._h, ptr, T, row * self.H * self.n_streams, row, row * self.H,
+                torch.cuda.current_stream(frames.device).cuda_stream,
+                recs.ctypes.data_as(ct.POINTER(nat.Blob)), bc, pts.ctypes.data_as(ct.POINTER(ct.c_int32)), pc,
+                counts.ctypes.data_as(ct.POINTER(ct.c_int32)))
+        else:
+            rc = self._L.gofpid_pipeline_process_host_sequence(
+                self._h, ptr, T, row * self.H * self.n_streams, row, row * self.H,
+                recs.ctypes.data_as(ct.POINTER(nat.Blob)), bc, pts.ctypes.data_as(ct.POINTER(ct.c_int32)), pc,
+                counts.ctypes.data_as(ct.POINTER(ct.c_int32)))
         if rc == nat.ERR_INVALID and "capacity" in nat.last_error():
             raise ValueError("blob_capacity / point_capacity too small for this clip: " + nat.last_error())
         nat.check(rc)
         nb, npt = int(counts[..., 0].sum()), int(counts[..., 1].sum())
         return counts, recs[:nb], pts[:npt]
+
+    def enqueue_device_sequence(self, ptr, n_frames, frame_stride, pitch, stream_stride, cuda_stream=0):
+        """A clip in DEVICE memory, enqueued only (gofpid_pipeline_process_device_sequence without
+        collection): the newest `depth` frames stay selectable afterwards."""
+        nat.check(self._L.gofpid_pipeline_process_device_sequence(
+            self._h, ptr, int(n_frames), int(frame_stride), int(pitch), int(stream_stride), cuda_stream,
+            None, 0, None, 0, None))
+
+    @property
+    def group(self):
+        """Frames per detector launch in the clip entry points (temporal blocking of MOG2)."""
+        return int(self._L.gofpid_pipeline_group(self._h))
 
     def blobs(self, stream=0, anchor="bottom"):
         """self.blobs_ of the reference (pipeline.py:555-588): list of dicts with keys
@@ -340,6 +361,12 @@ class HotPath:
 
     def launch_count(self):
         return int(self._L.gofpid_pipeline_launch_count(self._h))
+
+    def launch_total(self):
+        """Kernels launched since creation / the last reset."""
+        n = ct.c_longlong(0)
+        nat.check(self._L.gofpid_pipeline_launch_total(self._h, ct.byref(n)))
+        return int(n.value)
 
 
 # ---------------------------------------------------------------------- stage-level wrappers

@@ -356,6 +356,75 @@ def test_sequence_call_equals_frame_by_frame_calls():
     a.close(); b.close()
 
 
+@pytest.mark.parametrize("group", [1, 2, 3, 4, 8])
+@pytest.mark.parametrize("H,W,C,sigma,blur", [(40, 260, 1, 6, ("gaussian", (3, 3), 4.0)), (37, 53, 3, 25, None),
+                                              (41, 331, 1, 25, ("box", (3, 3))), (24, 200, 3, 6, ("gaussian", (5, 5), 4.0))])
+def test_mog2_frame_groups_bitexact(group, H, W, C, sigma, blur, monkeypatch):
+    """Temporal blocking: the clip entry point carries every tile through `group` frames per MOG2
+    launch (modes resident in shared memory).  Masks of EVERY frame and the model state stay
+    bit-exact against the oracle, through the early learning-rate schedule (n < 250) and beyond."""
+    import torch
+    monkeypatch.setenv("GOFPID_MOG2_GROUP", str(group))
+    monkeypatch.setenv("GOFPID_DEPTH", "16")
+    hp = _hot(_shape(H, W, C), blur=blur, detector="MOG2", morph=(), find_blobs=False)
+    assert hp.group == group and hp.depth == 16
+    ora = cport.MOG2(H, W, C)
+    clip = SyntheticClip(H, W, C, seed=7 * C + sigma, n_obj=4, noise_sigma=sigma)
+    sh = torch.cuda.current_stream().cuda_stream
+    row = W * C
+    done = 0
+    for chunk in (16, 11, 8, 1, 13, 16, 16, 16, 16, 7, 16, 16, 16, 16, 16, 16, 16, 16, 16, 16, 16, 5, 16):
+        frames = np.stack(clip.frames(chunk))
+        want = []
+        for f in frames:
+            g = f
+            if blur is not None:
+                g = cport.gaussian_blur(f, blur[1], blur[2]) if blur[0] == "gaussian" else cport.box_blur(f, blur[1])
+            want.append(ora.apply(g))
+        dev = torch.from_numpy(frames).cuda()
+        hp.enqueue_device_sequence(dev.data_ptr(), chunk, row * H, row, row * H, sh)
+        for age in range(chunk):
+            hp.select(age)
+            got = hp.mask()
+            assert np.array_equal(got, want[chunk - 1 - age]), (done, chunk, age, int((got != want[chunk - 1 - age]).sum()))
+        hp.select(0)
+        done += chunk
+        w, v, m, k = hp.mog2_model()
+        ow, ov, om, ok = ora.planes()
+        assert np.array_equal(k, ok), done
+        live = np.arange(5)[None, None, :] < ok[..., None]
+        assert np.array_equal(w[live], ow[live]) and np.array_equal(v[live], ov[live]) and np.array_equal(m[live], om[live]), done
+    assert done > 300
+    hp.close()
+
+
+def test_device_clip_equals_host_clip_and_streams_stay_independent():
+    """process_sequence on a CUDA tensor (gofpid_pipeline_process_device_sequence) returns what the
+    host clip call returns, with several streams per handle and frame groups."""
+    import torch
+    H, W, S, T = 72, 136, 3, 41
+    r3 = np.ones((3, 3), np.uint8)
+    kw = dict(blur=("gaussian", (3, 3), 4.0), detector="MOG2", morph=[("erode", r3), ("dilate", r3)], area_min=20.0,
+              n_streams=S)
+    clips = [SyntheticClip(H, W, 1, seed=50 + i, n_obj=4).frames(T) for i in range(S)]
+    clip = np.stack([np.stack(c) for c in clips], axis=1)  # (T, S, H, W)
+    a, b = _hot((H, W), **kw), _hot((H, W), **kw)
+    ca, ra, pa = a.process_sequence(clip)
+    cb, rb, pb = b.process_sequence(torch.from_numpy(clip).cuda())
+    assert np.array_equal(ca, cb) and np.array_equal(pa, pb) and ra.tobytes() == rb.tobytes()
+    assert a.launch_total() == b.launch_total() > 0
+    # and frame by frame on single-stream handles
+    for i in range(S):
+        kw1 = dict(kw, n_streams=1)
+        c = _hot((H, W), **kw1)
+        for t in range(T):
+            c.process(clip[t, i])
+            assert ca[t, i, 0] == len(c.raw_blobs()[0]), (i, t)
+        assert np.array_equal(c.mask(), a.mask(i))
+        c.close()
+    a.close(); b.close()
+
+
 def test_blob_capacity_overflow_is_reported():
     from pygofpid_b200._native import GofpidError
     H, W = 64, 64
