@@ -188,12 +188,14 @@ def peaks():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def traffic_per_launch(name):
-    """dram bytes per launch of the dominant kernel from the committed ncu capture, if any."""
+def traffic_per_launch(name, workload, streams, frames_per_launch):
+    """dram bytes per launch of the dominant kernel from the committed ncu capture (taken on the
+    headline workload, one stream, profiles/traffic.json's frames per launch); None otherwise."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(p):
+    if os.path.exists(p) and workload == DEFAULT_WORKLOAD and streams == 1:
         try:
-            return json.load(open(p)).get(name)
+            d = json.load(open(p))
+            return d.get(name) if d.get("_frames_per_launch", 1) == frames_per_launch else None
         except Exception:
             return None
     return None
@@ -399,7 +401,7 @@ def main():
             "e2e": e2e_obj,
             "gpu_launches": launches,
             "roofline": {"bound": "hbm", "kernel": kname, "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic_per_launch(kname),
+                         "frac": achieved / peak, "traffic": traffic_per_launch(kname, args.workload, S, G),
                          "peak_source": peak_src, "kernel_ms": det, "algorithmic_bytes": alg_bytes,
                          "bytes_per_pixel": bpp, "mean_modes": nbar, "frames_per_launch": G,
                          "kernel_us_per_frame": det * 1e3 / G,
