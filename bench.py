@@ -277,7 +277,7 @@ def main():
     e1.record(stream)
     barrier()
     dev_ms = e0.elapsed_time(e1)
-    launches = hp.launch_total() - l0
+    launches = (hp.launch_total() - l0) * world  # every rank launches the same kernels on its own streams
     info = hp.frame_info()
 
     # ---- timed: end to end through the host entry points (pinned frames in, blob lists out) ----

@@ -80,7 +80,7 @@ struct gofpid_pipeline {
     long long launches_total = 0;         // kernels launched since creation / reset
     int prefix_kept = 0, prefix_points = 0; // blob records / contour points copied to the host with every step
     cudaStream_t stream_c = nullptr; // result fetches
-    cudaStream_t stream_h = nullptr; // host->device frame copies
+    cudaStream_t stream_h = nullptr; // host->device frame copies (a second copy stream was measured: no gain)
     BlurParams blur;
     Mog2Params mog2p;
     KnnParams knnp;
@@ -104,6 +104,7 @@ struct gofpid_pipeline {
     size_t frames_pitch = 0, frames_stream = 0;
     const uint8_t *pinned_lo = nullptr, *pinned_hi = nullptr; // host range last found to be page-locked
     uint8_t *h_frames = nullptr; // pinned staging for pageable input
+    uint8_t *d_frames_base = nullptr; // device staging of all slots (slot i at i * frames_stream * n_streams)
 
     bool profiling = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -217,7 +218,6 @@ void free_all(gofpid_pipeline *p)
         run_list_free(&S.blobs.runs);
         cudaFree(S.blobs.labels); cudaFree(S.blobs.slot); cudaFree(S.blobs.comp); cudaFree(S.blobs.bitimg);
         cudaFree(S.blobs.info); cudaFree(S.blobs.kept); cudaFree(S.blobs.points);
-        cudaFree(S.d_frames);
         if (S.h_info) cudaFreeHost(S.h_info);
         if (S.h_kept) cudaFreeHost(S.h_kept);
         if (S.h_points) cudaFreeHost(S.h_points);
@@ -229,6 +229,7 @@ void free_all(gofpid_pipeline *p)
         if (S.graph_a) cudaGraphDestroy(S.graph_a);
         if (S.graph_b) cudaGraphDestroy(S.graph_b);
     }
+    cudaFree(p->d_frames_base);
     if (p->h_frames) cudaFreeHost(p->h_frames);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
     for (cudaStream_t s : {p->stream, p->stream_c, p->stream_h})
@@ -699,9 +700,13 @@ int stage_host_frames(gofpid_pipeline *p, int ahead, const uint8_t *h_frames, si
         p->frames_pitch = round_up(row, 128);
         p->frames_stream = p->frames_pitch * p->H;
     }
-    if (!F.d_frames)
-        for (int si = 0; si < p->depth; si++) // (all slots at once: no allocation inside a running pipeline)
-            if (!p->slots[si].d_frames) GOFPID_CUDA_TRY(cudaMalloc(&p->slots[si].d_frames, p->frames_stream * p->n_streams));
+    if (!F.d_frames) {
+        // all slots at once (no allocation inside a running pipeline), one block: consecutive slots are
+        // consecutive in memory, so a group of frames can arrive with one copy (stage_host_group)
+        const size_t per_slot = p->frames_stream * p->n_streams;
+        GOFPID_CUDA_TRY(cudaMalloc(&p->d_frames_base, per_slot * p->depth));
+        for (int si = 0; si < p->depth; si++) p->slots[si].d_frames = p->d_frames_base + per_slot * si;
+    }
     bool pinned = h_frames >= p->pinned_lo && h_frames < p->pinned_hi;
     if (!pinned) {
         cudaPointerAttributes attr;
@@ -736,6 +741,41 @@ int stage_host_frames(gofpid_pipeline *p, int ahead, const uint8_t *h_frames, si
     }
     GOFPID_CUDA_TRY(cudaEventRecord(F.ev_h2d, sh));
     GOFPID_CUDA_TRY(cudaStreamWaitEvent(p->stream, F.ev_h2d, 0));
+    return GOFPID_OK;
+}
+
+// g consecutive frames of a dense pinned clip -> g consecutive slots with ONE copy (a 2 MB frame
+// alone does not reach the link's bandwidth); anything else goes frame by frame.
+int stage_host_group(gofpid_pipeline *p, int g, const uint8_t *h_frames, size_t frame_stride, size_t pitch,
+                     size_t stream_stride)
+{
+    const size_t row = (size_t)p->W * p->Csrc;
+    const int s0 = (int)(p->frames % p->depth);
+    bool one = g > 1 && s0 + g <= p->depth && p->d_frames_base && pitch >= row &&
+               (p->n_streams == 1 || stream_stride == pitch * (size_t)p->H) &&
+               frame_stride == pitch * (size_t)p->H * p->n_streams;
+    if (one) {
+        cudaPointerAttributes a0, a1;
+        one = cudaPointerGetAttributes(&a0, h_frames) == cudaSuccess && a0.type == cudaMemoryTypeHost &&
+              cudaPointerGetAttributes(&a1, h_frames + frame_stride * (size_t)g - 1) == cudaSuccess &&
+              a1.type == cudaMemoryTypeHost;
+        if (!one) cudaGetLastError();
+    }
+    if (!one) {
+        for (int f = 0; f < g; f++)
+            GOFPID_TRY(stage_host_frames(p, f, h_frames + (size_t)f * frame_stride, pitch, stream_stride));
+        return GOFPID_OK;
+    }
+    cudaStream_t sh = p->stream_h;
+    for (int f = 0; f < g; f++) { // stage A of the slots' previous frames must have finished reading the staging
+        FrameSlot &F = p->slots[s0 + f];
+        if (F.used) GOFPID_CUDA_TRY(cudaStreamWaitEvent(sh, F.ev_mask, 0));
+    }
+    GOFPID_CUDA_TRY(cudaMemcpy2DAsync(p->slots[s0].d_frames, p->frames_pitch, h_frames, pitch, row,
+                                      (size_t)p->H * p->n_streams * g, cudaMemcpyHostToDevice, sh));
+    FrameSlot &L = p->slots[s0 + g - 1];
+    GOFPID_CUDA_TRY(cudaEventRecord(L.ev_h2d, sh));
+    GOFPID_CUDA_TRY(cudaStreamWaitEvent(p->stream, L.ev_h2d, 0));
     return GOFPID_OK;
 }
 
@@ -780,15 +820,9 @@ int run_sequence(gofpid_pipeline *p, const uint8_t *frames, bool host, int n_fra
         // frames t .. t+g-1 take the slots of frames t-depth .. t+g-1-depth: collect those first
         if (h_counts) GOFPID_TRY(collect(t + g - 1 - p->depth));
         const uint8_t *ptr[MOG2_MAX_GROUP];
-        for (int f = 0; f < g; f++) {
-            const uint8_t *src = frames + (size_t)(t + f) * frame_stride;
-            if (host) {
-                GOFPID_TRY(stage_host_frames(p, f, src, pitch, stream_stride));
-                ptr[f] = p->slots[(p->frames + f) % p->depth].d_frames;
-            } else {
-                ptr[f] = src;
-            }
-        }
+        if (host) GOFPID_TRY(stage_host_group(p, g, frames + (size_t)t * frame_stride, frame_stride, pitch, stream_stride));
+        for (int f = 0; f < g; f++)
+            ptr[f] = host ? p->slots[(p->frames + f) % p->depth].d_frames : frames + (size_t)(t + f) * frame_stride;
         if (host) GOFPID_TRY(run_group(p, ptr, g, p->frames_pitch, p->frames_stream, p->stream));
         else GOFPID_TRY(run_group(p, ptr, g, pitch, stream_stride, s));
         t += g;
