@@ -1376,6 +1376,34 @@ static int launch_fallback(const BlobBuffers &B, ImageU8 mask, int H, int W, int
     return GOFPID_OK;
 }
 
+// Results of a frame -> pinned host memory, written by the SMs (the host buffers are mapped into the
+// device's address space): exactly the records and points the frame produced, and no copy-engine
+// work that would queue up with the host->device frame copies.
+__global__ void __launch_bounds__(256)
+results_to_host_kernel(const gofpid_frame_info *info, const gofpid_blob *kept, const int32_t *points,
+                       gofpid_frame_info *h_info, gofpid_blob *h_kept, int32_t *h_points, int max_kept, int max_points)
+{
+    const int z = blockIdx.y;
+    const int nk = min(max(info[z].n_kept, 0), max_kept), np = min(max(info[z].n_points, 0), max_points);
+    const int t = blockIdx.x * blockDim.x + threadIdx.x, nt = gridDim.x * blockDim.x;
+    static_assert(sizeof(gofpid_frame_info) == 32 && sizeof(gofpid_blob) == 64, "records are copied as 16-byte words");
+    if (t < 2) reinterpret_cast<uint4 *>(h_info + z)[t] = reinterpret_cast<const uint4 *>(info + z)[t];
+    const uint4 *ks = reinterpret_cast<const uint4 *>(kept + (size_t)z * max_kept);
+    uint4 *kd = reinterpret_cast<uint4 *>(h_kept + (size_t)z * max_kept);
+    for (int i = t; i < nk * 4; i += nt) kd[i] = ks[i];
+    const uint2 *ps = reinterpret_cast<const uint2 *>(points + (size_t)z * max_points * 2);
+    uint2 *pd = reinterpret_cast<uint2 *>(h_points + (size_t)z * max_points * 2);
+    for (int i = t; i < np; i += nt) pd[i] = ps[i];
+}
+int launch_results_to_host(const BlobBuffers &B, gofpid_frame_info *h_info, gofpid_blob *h_kept, int32_t *h_points,
+                           int n_streams, cudaStream_t s)
+{
+    const dim3 grid(n_streams == 1 ? 8 : (n_streams <= 8 ? 4 : 2), n_streams);
+    results_to_host_kernel<<<grid, 256, 0, s>>>(B.info, B.kept, B.points, h_info, h_kept, h_points, B.max_kept, B.max_points);
+    GOFPID_CUDA_TRY(cudaGetLastError());
+    return GOFPID_OK;
+}
+
 int launch_blobs(const BlobBuffers &B, ImageU8 mask, int H, int W, int n_streams,
                  const FrameTick *tick, cudaStream_t s, int *n_launches, bool bits_ready,
                  const cudaGraphConditionalHandle *cond)

@@ -264,6 +264,9 @@ struct BlobBuffers {
 int launch_blobs(const BlobBuffers &B, ImageU8 mask, int H, int W, int n_streams,
                  const FrameTick *tick, cudaStream_t s, int *n_launches, bool bits_ready,
                  const cudaGraphConditionalHandle *cond = nullptr);
+// h_*: device-side addresses of the pinned host mirrors (cudaHostGetDevicePointer)
+int launch_results_to_host(const BlobBuffers &B, gofpid_frame_info *h_info, gofpid_blob *h_kept, int32_t *h_points,
+                           int n_streams, cudaStream_t s);
 int launch_fill_labels(const RunList &R, int z, const gofpid_frame_info *info, int32_t *labels, size_t LP,
                        cudaStream_t s);
 int launch_canonical_labels(const uint8_t *mask, size_t mask_pitch, const int32_t *labels, size_t LP,
