@@ -187,7 +187,7 @@ struct Mog2Args {
 int launch_mog2(const DetectLaunch &L, Mog2Model model, const Mog2Params &mp, FrameTick *tick,
                 const Mog2Group *grp = nullptr);
 void mog2_prepare_lr(const Mog2Params &mp, long n_done, float (*lr)[4]); // rates of frames n_done+1 ..
-const void *mog2_kernel_func(int C);
+const void *mog2_kernel_func(int C, int H, int W);
 void mog2_kernel_params(Mog2Args &a, void **params); // params[9]
 int launch_knn(const DetectLaunch &L, KnnModel model, const KnnParams &kp,
                const uint64_t *d_jump_table);

@@ -495,7 +495,7 @@ int build_graphs(gofpid_pipeline *p, FrameSlot &F, const FrameSrc &src)
         if (t != cudaGraphNodeTypeKernel) continue;
         cudaKernelNodeParams kp;
         GOFPID_CUDA_TRY(cudaGraphKernelNodeGetParams(nodes[i], &kp));
-        const void *want = p->cfg.detector == GOFPID_DETECT_MOG2 ? mog2_kernel_func(p->C) : tick_kernel_func();
+        const void *want = p->cfg.detector == GOFPID_DETECT_MOG2 ? mog2_kernel_func(p->C, p->H, p->W) : tick_kernel_func();
         if (kp.func == want) { F.tick_node = nodes[i]; F.src_node_params = kp; break; }
     }
     if (!F.tick_node) { set_error("graph capture: frame-source node not found"); return GOFPID_ERR_CUDA; }
