@@ -122,7 +122,9 @@ struct Mog2Group {
     const uint8_t *frame[MOG2_MAX_GROUP]; // frame f of the group (stream 0; FrameSrc::pitch / stream_stride apply)
     uint8_t *mask[MOG2_MAX_GROUP];        // detector mask of frame f (stream 0; ImageU8::pitch / stream_stride apply)
     int nf;                               // frames in this launch (1 .. MOG2_MAX_GROUP)
+    int aligned4;                         // pitch, stream stride and every frame pointer are multiples of 4 (set by the launcher)
 };
+int mog2_group_aligned4(const Mog2Group &g, const FrameSrc &src);
 struct Mog2Model {
     float *planes;      // [stream][tile][5][2 + C][512]
     uint8_t *nmodes;    // [stream][tile][512]

@@ -434,6 +434,7 @@ int enqueue_stage_a(gofpid_pipeline *p, FrameSlot &F, const FrameSrc &src, cudaS
         Mog2Group one;
         memset(&one, 0, sizeof(one));
         one.frame[0] = src.base; one.mask[0] = L.mask.base; one.nf = 1;
+        one.aligned4 = mog2_group_aligned4(one, src);
         F.mog2_args = Mog2Args{L.blur, L.mask, p->mog2, p->mog2p, p->d_tick, src, one, p->H, p->W};
     }
     else if (p->cfg.detector == GOFPID_DETECT_KNN) GOFPID_TRY(launch_knn(L, p->knn, p->knnp, p->d_pow2tab));
@@ -559,6 +560,7 @@ int run_step(gofpid_pipeline *p, const uint8_t *d_frames, size_t pitch, size_t s
             if (p->cfg.detector == GOFPID_DETECT_MOG2) {
                 F.mog2_args.src = src;
                 F.mog2_args.grp.frame[0] = src.base;
+                F.mog2_args.grp.aligned4 = mog2_group_aligned4(F.mog2_args.grp, src);
                 mog2_kernel_params(F.mog2_args, params);
             } else {
                 p->tick_args.src = src;
