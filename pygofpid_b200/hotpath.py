@@ -293,23 +293,7 @@ class HotPath:
         """self.blobs_ of the reference (pipeline.py:555-588): list of dicts with keys
         contour (int32 (N,1,2)), anchor / bottom / center (int16 (2,))."""
         recs, pts = self.raw_blobs(stream)
-        out = []
-        for b in recs:
-            contour = pts[b.point_offset:b.point_offset + b.n_points].reshape(-1, 1, 2).copy()
-            # cv.moments of a contour (helpers.py:156,165): m00 = a00/2, m10 = a10/6, m01 = a01/6,
-            # with the sign of a00 folded into the factors
-            a00, a10, a01 = float(b.a00), float(b.a10), float(b.a01)
-            if a00 > 0:
-                h, s = 0.5, 0.16666666666666666666666666666667
-            else:
-                h, s = -0.5, -0.16666666666666666666666666666667
-            m00, m10, m01 = a00 * h, a10 * s, a01 * s
-            cx = int(m10 / m00)
-            bottom = np.array([cx, b.y1], dtype=np.int16)
-            center = np.array([cx, int(m01 / m00)], dtype=np.int16)
-            out.append(dict(contour=contour, anchor=bottom if anchor == "bottom" else center,
-                            bottom=bottom, center=center))
-        return out
+        return [_blob_dict(pts, b.point_offset, b.n_points, b.y1, b.a00, b.a10, b.a01, anchor) for b in recs]
 
     # ------------------------------------------------------------------ model state
     def mog2_model(self, stream=0):
@@ -367,6 +351,30 @@ class HotPath:
         n = ct.c_longlong(0)
         nat.check(self._L.gofpid_pipeline_launch_total(self._h, ct.byref(n)))
         return int(n.value)
+
+
+def _blob_dict(pts, point_offset, n_points, y1, a00, a10, a01, anchor):
+    """One entry of the reference's blobs_ (pipeline.py:572-588) from a gofpid_blob record."""
+    contour = pts[point_offset:point_offset + n_points].reshape(-1, 1, 2).copy()
+    # cv.moments of a contour (helpers.py:156,165): m00 = a00/2, m10 = a10/6, m01 = a01/6,
+    # with the sign of a00 folded into the factors
+    a00, a10, a01 = float(a00), float(a10), float(a01)
+    if a00 > 0:
+        h, s = 0.5, 0.16666666666666666666666666666667
+    else:
+        h, s = -0.5, -0.16666666666666666666666666666667
+    m00, m10, m01 = a00 * h, a10 * s, a01 * s
+    cx = int(m10 / m00)
+    bottom = np.array([cx, y1], dtype=np.int16)
+    center = np.array([cx, int(m01 / m00)], dtype=np.int16)
+    return dict(contour=contour, anchor=bottom if anchor == "bottom" else center, bottom=bottom, center=center)
+
+
+def blobs_from_records(recs, pts, anchor="bottom"):
+    """blobs_ lists from one frame's slice of process_sequence's output (records: BLOB_DTYPE rows,
+    pts: that frame's contour points; point_offset restarts at 0 for every frame)."""
+    return [_blob_dict(pts, int(b['point_offset']), int(b['n_points']), int(b['y1']), int(b['a00']), int(b['a10']),
+                       int(b['a01']), anchor) for b in recs]
 
 
 # ---------------------------------------------------------------------- stage-level wrappers

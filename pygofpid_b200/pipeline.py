@@ -308,6 +308,46 @@ class GOFPID():
         y = self._detect_blob()  # step 7
         return self._maintain_alarm(y)
 
+    def detect_clip(self, X):
+        """A decoded clip (T, H, W[, C]) at once -- the read-detect loop of examples/video.py:45-50
+        without one synchronous GPU round trip per frame: steps 1-4 of all frames go through the
+        library's clip entry point (frames in flight, MOG2 carried through several frames per
+        launch), steps 5-7 run per frame on the host as in `detect`.  Not part of the reference's
+        API; returns what `detect` would have returned frame by frame (list of bool) and leaves
+        `blobs_`, `tracked_blobs_` and `foreground_mask_` as after the last frame."""
+        X = np.asarray(X)
+        if X.ndim < 3 or X.shape[0] == 0:
+            raise ValueError('a clip is an array of frames: (T, H, W) or (T, H, W, C)')
+        fused = None
+        if self.convert and self._host_estimator is None and X.ndim == 4 and X.shape[3] == 3 \
+                and X.dtype == np.uint8:
+            fused = {_COLOR_BGR2GRAY: "bgr2gray", _COLOR_RGB2GRAY: "rgb2gray"}.get(self.convert)
+        if self._host_estimator is not None or (self.convert and fused is None) or X.dtype != np.uint8:
+            return [self.detect(f) for f in X]  # host estimator / host-side conversion: frame by frame
+        if not self.input_shape_:
+            self.input_shape_ = X.shape[1:]
+            self._calib_first_frame()
+        elif X.shape[1:] != self.input_shape_:
+            raise ValueError('Input shape has changed.')
+        if self._engine is None:
+            self._engine = self._new_engine(X.shape[1:], self.frg_detect, self._plan['blur'],
+                                            self._plan['morph'], fused)
+        from .hotpath import blobs_from_records
+        frames = X[..., 0] if (X.ndim == 4 and X.shape[3] == 1) else X
+        counts, recs, pts = self._engine.process_sequence(frames)
+        self._mask_cache = None
+        out, ob, op = [], 0, 0
+        for t in range(X.shape[0]):
+            nb, npt = int(counts[t, 0, 0]), int(counts[t, 0, 1])
+            self.blobs_ = blobs_from_records(recs[ob:ob + nb], pts[op:op + npt], self.post_filter['anchor'])
+            ob += nb
+            op += npt
+            self._track_blob()       # step 5
+            self._post_filter()      # step 6
+            y = self._detect_blob()  # step 7
+            out.append(self._maintain_alarm(y))
+        return out
+
     def _convert(self, X):
         if self.convert in (_COLOR_BGR2GRAY, _COLOR_RGB2GRAY) and X.ndim == 3 and X.shape[2] == 3 \
                 and X.dtype == np.uint8:
