@@ -20,6 +20,8 @@ The OpenCV callables of the reference's parameter dicts (`cv.GaussianBlur`, `cv.
 identity / name; their string names work too when OpenCV is not installed.  There is no CPU
 fallback for steps 1-4: anything the kernels do not cover raises NotImplementedError.
 """
+import math
+
 import numpy as np
 
 from .helpers import (SimpleLinearRegression, normalize_coords, point_in_polygon, read_first_frame,
@@ -416,6 +418,10 @@ class GOFPID():
             self._perspective[key] = slr.fit(bottoms, values).predict_clip(rows, 0)
 
     def _predict_perspective(self, key, y):
+        if np.ndim(y) == 0:  # one ordinate: the same clip and lookup without numpy's scalar overhead
+            yi = int(y)
+            last = self.input_shape_[0] - 1
+            return self._perspective.get(key)[0 if yi < 0 else (last if yi > last else yi)]
         y = np.clip(y, a_min=0, a_max=self.input_shape_[0] - 1)
         return self._perspective.get(key)[y]
 
@@ -462,12 +468,12 @@ class GOFPID():
 
     def _relative_travel(self, track):
         """Distance between first and last centre, in units of sqrt(expected person area)."""
-        delta = np.asarray(track['center'], dtype=np.float64) - np.asarray(track['center_first'],
-                                                                          dtype=np.float64)
+        c, c0 = track['center'], track['center_first']
+        dx, dy = float(c[0]) - float(c0[0]), float(c[1]) - float(c0[1])  # float64, like the reference's norm
         area_min = self._predict_perspective('area', track['bottom'][1])
         if area_min <= 0:
             return 0
-        return float(np.sqrt((delta * delta).sum())) / np.sqrt(area_min)
+        return math.sqrt(dx * dx + dy * dy) / math.sqrt(area_min)
 
     def _pair(self, track, blob):
         track.update(contour=blob['contour'].copy(), anchor=blob['anchor'], bottom=blob['bottom'],
