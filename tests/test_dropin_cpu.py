@@ -163,3 +163,31 @@ def test_tracking_distance_matrix_equals_the_scalar_code():
             want = np.array([[g._tracking_distance(t, b) for t in tracks] for b in blobs], dtype=np.float64)
             got = g._tracking_distance_matrix(tracks, blobs)
             assert np.array_equal(got, want, equal_nan=True), trial
+
+
+@pytest.mark.parametrize("name", ["fd_gray_open3", "mog2_gray_default", "mog2_bgr_default", "knn_gray_default",
+                                  "mog2_gray_box_openclose", "mog2_gray_convert_bgr"])
+def test_host_tail_replays_the_reference_tracks_and_alarms(name):
+    """Steps 5-7 (tracking, post-filter, alarm: reference pipeline.py:590-799) on the host, fed with
+    the blob lists the REAL reference produced (tests/golden/*.npz): the number of tracked blobs and
+    the alarm of every frame are the reference's.  No GPU involved."""
+    from golden_cases import golden_blobs, load
+    g = load(name)
+    H, W, C = (int(v) for v in g["shape"])
+    pf = {'perimeter': None, 'anchor': 'bottom', 'perspective': None, 'perspective_coeff': 0.5,
+          'presence_min': 3, 'distance_min': 0.25}
+    gofpid = GOFPID(post_filter=pf).initialize()
+    gofpid.input_shape_ = (H, W) if C == 1 else (H, W, C)
+    gofpid._calib_first_frame()
+    for t in range(int(g["n"])):
+        blobs = golden_blobs(g, t)
+        for b in blobs:
+            b["center"] = np.asarray(b["center"], np.int16)
+            b["bottom"] = np.asarray(b["bottom"], np.int16)
+            b["anchor"] = b["bottom"]
+        gofpid.blobs_ = blobs
+        gofpid._track_blob()
+        gofpid._post_filter()
+        y = gofpid._maintain_alarm(gofpid._detect_blob())
+        assert bool(y) == bool(g["alarm"][t]), (name, t)
+        assert len(gofpid.tracked_blobs_) == int(g["ntracked"][t]), (name, t)
