@@ -34,7 +34,7 @@ def point_in_polygon(polygon, point):
     """+1 inside, 0 on the boundary, -1 outside (what cv.pointPolygonTest(..., False) answers).
 
     Exact integer / float arithmetic on the polygon's vertices (even-odd rule)."""
-    poly = np.asarray(polygon, dtype=np.float64).reshape(-1, 2)
+    poly = np.asarray(polygon, dtype=np.float64).reshape(-1, 2).tolist()  # (plain floats: same doubles, faster)
     px, py = float(point[0]), float(point[1])
     n = len(poly)
     inside = False

@@ -506,15 +506,22 @@ class GOFPID():
                 self._miss(j)
             return
         dist = self._tracking_distance_matrix(tracks, blobs)
+        # (a blob's row is only read for that blob: nearest tracks of all rows at once)
+        nearest = dist.argmin(axis=1).tolist()
+        inside = (dist[np.arange(len(blobs)), nearest] <= 1).tolist()
+        paired = [False] * n_tracks
         for i, blob in enumerate(blobs):
-            j = int(np.argmin(dist[i]))
-            if dist[i, j] <= 1:
-                dist[i, j] = -1  # marks the pair
-                self._pair(tracks[j], blob)
+            if inside[i]:
+                paired[nearest[i]] = True
+                self._pair(tracks[nearest[i]], blob)
             else:
                 tracks.append(self._new_track(blob))
+        # tracks no blob was paired with age.  The reference marks a pair with dist = -1 and ages the
+        # tracks whose column satisfies all(dist >= 0): a column that already held a negative value
+        # (int16 wrap-around of the squared differences) or a NaN is not aged either
+        nonneg = (dist >= 0).all(axis=0).tolist()
         for j in range(n_tracks - 1, -1, -1):
-            if np.all(dist[:, j] >= 0):
+            if nonneg[j] and not paired[j]:
                 self._miss(j)
 
     # ------------------------------------------------------------------ steps 6-7
@@ -527,8 +534,9 @@ class GOFPID():
             else:
                 track['filtered'].discard('perimeter')
             xy = track['contour'].reshape(-1, 2)
-            width = int(xy[:, 0].max()) - int(xy[:, 0].min()) + 1
-            height = int(xy[:, 1].max()) - int(xy[:, 1].min()) + 1
+            lo, hi = xy.min(axis=0), xy.max(axis=0)  # cv.boundingRect of the contour
+            width = int(hi[0]) - int(lo[0]) + 1
+            height = int(hi[1]) - int(lo[1]) + 1
             if width * height <= self._predict_perspective('area', track['bottom'][1]) * pf['perspective_coeff']:
                 track['filtered'].add('perspective')
             else:
