@@ -191,3 +191,30 @@ def test_host_tail_replays_the_reference_tracks_and_alarms(name):
         y = gofpid._maintain_alarm(gofpid._detect_blob())
         assert bool(y) == bool(g["alarm"][t]), (name, t)
         assert len(gofpid.tracked_blobs_) == int(g["ntracked"][t]), (name, t)
+
+
+@pytest.mark.parametrize("trial", range(12))
+def test_host_tail_matches_the_reference_on_busy_blob_streams(trial):
+    """Up to 30 moving blobs with missed detections, three frame sizes, two post-filter settings
+    (perimeter polygon + perspective boxes / defaults): alarm, number of tracks, summed presence and
+    number of active filters per frame are what the REAL reference's tail answered
+    (tests/golden/tail_streams.npz, generated by tests/golden/make_tail_golden.py)."""
+    import os
+    import warnings
+    from golden_cases import GOLDEN_DIR, tail_post_filter, tail_stream
+    want = np.load(os.path.join(GOLDEN_DIR, "tail_streams.npz"))
+    H, W, kind, frames = tail_stream(trial)
+    g = GOFPID(post_filter=tail_post_filter(kind)).initialize()
+    g.input_shape_ = (H, W)
+    g._calib_first_frame()
+    for t, blobs in enumerate(frames):
+        g.blobs_ = blobs
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            g._track_blob()
+            g._post_filter()
+            y = g._maintain_alarm(g._detect_blob())
+        assert bool(y) == bool(want["alarm_%d" % trial][t]), t
+        assert len(g.tracked_blobs_) == int(want["ntracked_%d" % trial][t]), t
+        assert sum(tr['presence'] for tr in g.tracked_blobs_) == int(want["presence_%d" % trial][t]), t
+        assert sum(len(tr['filtered']) for tr in g.tracked_blobs_) == int(want["nfiltered_%d" % trial][t]), t
