@@ -11,7 +11,8 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, os.path.dirname(HERE))
 sys.path.insert(0, "/root/reference")
-from golden_cases import TAIL_FRAMES, TAIL_TRIALS, tail_post_filter, tail_stream  # noqa: E402
+from golden_cases import (DISPLAY_FRAMES, DISPLAY_TRIALS, TAIL_FRAMES, TAIL_TRIALS, tail_post_filter,  # noqa: E402
+                          tail_stream)
 from pygofpid.pipeline import GOFPID  # noqa: E402  (the real reference)
 
 out = {}
@@ -21,7 +22,7 @@ for trial in range(TAIL_TRIALS):
     g.input_shape_ = (H, W)
     g._calib_first_frame()
     alarm, ntracked, presence, nfiltered = [], [], [], []
-    for blobs in frames:
+    for t, blobs in enumerate(frames):
         g.blobs_ = blobs
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
@@ -30,8 +31,12 @@ for trial in range(TAIL_TRIALS):
             y = g._maintain_alarm(g._detect_blob())
         alarm.append(bool(y))
         ntracked.append(len(g.tracked_blobs_))
-        presence.append(sum(t['presence'] for t in g.tracked_blobs_))
-        nfiltered.append(sum(len(t['filtered']) for t in g.tracked_blobs_))
+        presence.append(sum(tr['presence'] for tr in g.tracked_blobs_))
+        nfiltered.append(sum(len(tr['filtered']) for tr in g.tracked_blobs_))
+        if trial in DISPLAY_TRIALS and t in DISPLAY_FRAMES:  # GOFPID.display draws into the frame in place
+            canvas = np.zeros((H, W, 3), np.uint8)
+            g.display(canvas, {'tracking': True, 'perspective': True})
+            out["display_%d_%d" % (trial, t)] = canvas
     out["alarm_%d" % trial] = np.array(alarm)
     out["ntracked_%d" % trial] = np.array(ntracked, np.int32)
     out["presence_%d" % trial] = np.array(presence, np.int32)

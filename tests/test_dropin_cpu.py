@@ -218,3 +218,34 @@ def test_host_tail_matches_the_reference_on_busy_blob_streams(trial):
         assert len(g.tracked_blobs_) == int(want["ntracked_%d" % trial][t]), t
         assert sum(tr['presence'] for tr in g.tracked_blobs_) == int(want["presence_%d" % trial][t]), t
         assert sum(len(tr['filtered']) for tr in g.tracked_blobs_) == int(want["nfiltered_%d" % trial][t]), t
+
+
+@pytest.mark.skipif(cv is None, reason="display() draws with OpenCV")
+@pytest.mark.parametrize("trial", [0, 3])
+def test_display_draws_what_the_reference_draws(trial):
+    """GOFPID.display (reference pipeline.py:801-853) draws perimeter, contours, anchors, tracking
+    ellipses and perspective boxes into the frame in place: same pixels as the REAL reference on the
+    same tracked blobs (canvases in tests/golden/tail_streams.npz)."""
+    import os
+    import warnings
+    from golden_cases import DISPLAY_FRAMES, GOLDEN_DIR, tail_post_filter, tail_stream
+    want = np.load(os.path.join(GOLDEN_DIR, "tail_streams.npz"))
+    H, W, kind, frames = tail_stream(trial)
+    g = GOFPID(post_filter=tail_post_filter(kind)).initialize()
+    g.input_shape_ = (H, W)
+    g._calib_first_frame()
+    seen = 0
+    for t, blobs in enumerate(frames):
+        g.blobs_ = blobs
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            g._track_blob()
+            g._post_filter()
+            g._maintain_alarm(g._detect_blob())
+        if t in DISPLAY_FRAMES:
+            canvas = np.zeros((H, W, 3), np.uint8)
+            g.display(canvas, {'tracking': True, 'perspective': True})
+            ref = want["display_%d_%d" % (trial, t)]
+            assert ref.any() and np.array_equal(canvas, ref), (trial, t, int((canvas != ref).sum()))
+            seen += 1
+    assert seen == len(DISPLAY_FRAMES)
