@@ -249,3 +249,14 @@ def test_display_draws_what_the_reference_draws(trial):
             assert ref.any() and np.array_equal(canvas, ref), (trial, t, int((canvas != ref).sum()))
             seen += 1
     assert seen == len(DISPLAY_FRAMES)
+
+
+def test_detect_clip_validates_its_input_before_touching_the_gpu():
+    g = make(frg_detect='MOG2').initialize()
+    with pytest.raises(ValueError):
+        g.detect_clip(np.zeros((0, 8, 8), np.uint8))   # no frames
+    with pytest.raises(ValueError):
+        g.detect_clip(np.zeros((8, 8), np.uint8))      # a frame, not a clip
+    g.input_shape_ = (8, 8)
+    with pytest.raises(ValueError, match="Input shape has changed"):
+        g.detect_clip(np.zeros((2, 9, 8), np.uint8))
