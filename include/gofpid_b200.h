@@ -116,6 +116,11 @@ typedef struct gofpid_config {
      * the path works on their gray value (cv.cvtColor's 15-bit fixed point), computed while the
      * frame is loaded.  The pipeline is created with C = 3. */
     int32_t convert;       /* GOFPID_CONVERT_* */
+
+    /* pipelining; 0 = default.  A synchronous caller (GOFPID.detect: one frame per call) never has
+     * more than one frame in flight and may ask for a shallow handle to save memory. */
+    int32_t depth;         /* frame slots = frames that can be in flight (1 .. 16; default 6, MOG2 12) */
+    int32_t mog2_group;    /* frames per MOG2 launch in the clip entry points (1 .. 8; default 3)   */
 } gofpid_config;
 
 /* One blob that passed the area filter (the device-side half of GOFPID._create_blob,
@@ -138,7 +143,9 @@ typedef struct gofpid_frame_info {
     int32_t n_candidates; /* external components passing the bbox pre-filter           */
     int32_t n_kept;       /* contours with contourArea >= area_min (incl. enclosed ones, see reserved[0]) */
     int32_t n_points;     /* contour points in the pool                                */
-    int32_t overflow;     /* bit0: components, bit1: kept blobs, bit2: points, bit3: internal */
+    int32_t overflow;     /* the frame did not fit the handle's per-slot capacities (bit0: components,
+                             bit1: kept blobs, bit2: points; gofpid_pipeline_blobs then re-runs blob
+                             creation on the frame's mask with buffers of the size it needs), bit3: internal */
     int32_t frame_index;  /* 1-based count of frames this stream has processed         */
     int32_t reserved[2];  /* [0]: how many of n_kept are enclosed by another blob (not returned)     */
 } gofpid_frame_info;
@@ -150,6 +157,13 @@ GOFPID_API const char *gofpid_version(void);
 GOFPID_API const char *gofpid_last_error(void);
 GOFPID_API int gofpid_device_count(void);
 GOFPID_API void gofpid_config_default(gofpid_config *cfg);
+
+/* Page-locked host memory for frames handed to the host entry points (submit_host, process_host,
+ * process_host_sequence): copies from it are asynchronous and run at the link's speed.  With
+ * write_combined != 0 the buffer is write-combined (fast for the device to read over PCIe, slow for
+ * the CPU to read back: fill it, do not read it).  Free with gofpid_host_free. */
+GOFPID_API int gofpid_host_alloc(size_t bytes, int write_combined, void **out);
+GOFPID_API int gofpid_host_free(void *ptr);
 
 /* 8.8 fixed-point taps cv.GaussianBlur uses for u8 images (n odd, <= GOFPID_MAX_KSIZE). */
 GOFPID_API int gofpid_gaussian_taps_q8(int n, double sigma, uint16_t *h_taps);
@@ -187,6 +201,13 @@ GOFPID_API int gofpid_pipeline_process_host_sequence(gofpid_pipeline *p, const u
                                                      int blob_capacity, int32_t *h_points,
                                                      int point_capacity, int32_t *h_counts);
 
+/* A clip call whose h_blobs / h_points were too small returns GOFPID_ERR_INVALID *after* the whole clip
+ * went through (the temporal model is where it should be, h_counts is complete) and keeps the blob
+ * lists of every frame of that clip in the handle: size the buffers from h_counts and fetch them here.
+ * The lists stay valid until the next clip call on the handle. */
+GOFPID_API int gofpid_pipeline_sequence_results(gofpid_pipeline *p, gofpid_blob *h_blobs, int blob_capacity,
+                                                int32_t *h_points, int point_capacity);
+
 /* The same for a clip that already is in device memory (frame t at d_frames + t * frame_stride);
  * the detector launches are enqueued on `stream`.  With h_counts == NULL nothing is collected: the
  * call only enqueues the work and the newest `depth` frames stay selectable (gofpid_pipeline_select).
@@ -199,6 +220,11 @@ GOFPID_API int gofpid_pipeline_process_device_sequence(gofpid_pipeline *p, const
                                                        gofpid_blob *h_blobs, int blob_capacity,
                                                        int32_t *h_points, int point_capacity,
                                                        int32_t *h_counts);
+/* Orders `stream` after everything the handle has enqueued so far -- the detector launches AND the
+ * morphology / blob kernels that run on the handle's internal streams -- without blocking the host
+ * (cudaStreamWaitEvent on every frame slot in flight).  An event recorded on `stream` afterwards marks
+ * the end of all that work: what a caller timing or chaining device-resident clips needs. */
+GOFPID_API int gofpid_pipeline_join(gofpid_pipeline *p, void *stream);
 /* Frames per detector launch in the clip entry points (1 unless the detector is MOG2). */
 GOFPID_API int gofpid_pipeline_group(gofpid_pipeline *p);
 
@@ -218,7 +244,10 @@ GOFPID_API int gofpid_pipeline_depth(gofpid_pipeline *p);
 GOFPID_API int gofpid_pipeline_frame_info(gofpid_pipeline *p, int stream_idx,
                                           gofpid_frame_info *h_info);
 /* Blobs in the reference's order (descending raster order of the first pixel) and their
- * contour points as (x, y) int32 pairs.  Capacities are in records / points. */
+ * contour points as (x, y) int32 pairs.  Capacities are in records / points; when they are too
+ * small the call returns GOFPID_ERR_INVALID with the sizes it needs in *n_blobs / *n_points.
+ * A frame that exceeded the handle's max_blobs / max_kept / max_points is not an error: blob
+ * creation is run again on the frame's (still resident) final mask with larger buffers. */
 GOFPID_API int gofpid_pipeline_blobs(gofpid_pipeline *p, int stream_idx, gofpid_blob *h_blobs,
                                      int blob_capacity, int32_t *h_points, int point_capacity,
                                      int *n_blobs, int *n_points);

@@ -49,6 +49,7 @@ class Config(ct.Structure):
         ("blob_area_min", ct.c_double),
         ("max_blobs", ct.c_int32), ("max_kept", ct.c_int32), ("max_points", ct.c_int32),
         ("convert", ct.c_int32),
+        ("depth", ct.c_int32), ("mog2_group", ct.c_int32),
     ]
 
 
@@ -77,6 +78,8 @@ SIGNATURES = {
     "gofpid_last_error": (ct.c_char_p, []),
     "gofpid_device_count": (ct.c_int, []),
     "gofpid_config_default": (None, [ct.POINTER(Config)]),
+    "gofpid_host_alloc": (ct.c_int, [_sz, ct.c_int, ct.POINTER(_vp)]),
+    "gofpid_host_free": (ct.c_int, [_vp]),
     "gofpid_gaussian_taps_q8": (ct.c_int, [ct.c_int, ct.c_double, ct.POINTER(ct.c_uint16)]),
     "gofpid_pipeline_create": (ct.c_int, [ct.POINTER(Config), ct.c_int, ct.c_int, ct.c_int, ct.c_int,
                                           ct.c_int, ct.POINTER(_vp)]),
@@ -90,6 +93,8 @@ SIGNATURES = {
     "gofpid_pipeline_process_device_sequence": (ct.c_int, [_vp, _vp, ct.c_int, _sz, _sz, _sz, _vp, ct.POINTER(Blob),
                                                            ct.c_int, ct.POINTER(ct.c_int32), ct.c_int,
                                                            ct.POINTER(ct.c_int32)]),
+    "gofpid_pipeline_sequence_results": (ct.c_int, [_vp, ct.POINTER(Blob), ct.c_int, ct.POINTER(ct.c_int32), ct.c_int]),
+    "gofpid_pipeline_join": (ct.c_int, [_vp, _vp]),
     "gofpid_pipeline_group": (ct.c_int, [_vp]),
     "gofpid_pipeline_select": (ct.c_int, [_vp, ct.c_int]),
     "gofpid_pipeline_depth": (ct.c_int, [_vp]),

@@ -1240,7 +1240,7 @@ nest_kernel(gofpid_frame_info *info, gofpid_blob *kept, const int32_t *points, i
 {
     constexpr int CAP = 2048; // boxes staged in shared memory (further blobs are read from global)
     __shared__ short4 box[CAP];
-    const int z = blockIdx.x;
+    const int z = blockIdx.y;
     gofpid_frame_info *fi = info + z;
     const int nk = min(fi->n_kept, max_kept);
     if (nk < 2) return;
@@ -1254,7 +1254,7 @@ nest_kernel(gofpid_frame_info *info, gofpid_blob *kept, const int32_t *points, i
         if (i < CAP) return box[i];
         return make_short4((short)kb[i].x0, (short)kb[i].y0, (short)kb[i].x1, (short)kb[i].y1);
     };
-    for (int k = warp; k < nk; k += nwarps) {
+    for (int k = blockIdx.x * nwarps + warp; k < nk; k += gridDim.x * nwarps) { // (several CTAs: frames with very many blobs)
         const short4 bk = get_box(k);
         bool nested = false;
         int fy = 0, fx = 0;
@@ -1328,13 +1328,10 @@ static int launch_labelling(ImageU8 mask, const uint32_t *bitimg, int bit_pitch,
                             const RunList &R, int32_t *labels, size_t LP, size_t labels_stream,
                             int32_t *comp, int max_blobs, int H, int W, int n_streams,
                             gofpid_frame_info *info, const FrameTick *tick, int force_tiled, cudaStream_t s,
-                            const cudaGraphConditionalHandle *cond)
+                            const cudaGraphConditionalHandle *cond, int runs_cap)
 {
     int max_runs = R.max_runs;
-    {
-        const char *e = getenv("GOFPID_RUNS_CAP"); // tests: force the tiled fallback with a tiny capacity
-        if (e && atoi(e) >= 0 && atoi(e) < max_runs) max_runs = atoi(e) & ~7;
-    }
+    if (runs_cap >= 0 && runs_cap < max_runs) max_runs = runs_cap & ~7; // tests: force the tiled fallback with a tiny capacity
     if (force_tiled) max_runs = 0;
     if (R.max_runs > 0) {
         runs_extract_kernel<<<dim3((H + RX_ROWS - 1) / RX_ROWS, n_streams), RX_THREADS, 0, s>>>(
@@ -1406,7 +1403,7 @@ int launch_results_to_host(const BlobBuffers &B, gofpid_frame_info *h_info, gofp
 
 int launch_blobs(const BlobBuffers &B, ImageU8 mask, int H, int W, int n_streams,
                  const FrameTick *tick, cudaStream_t s, int *n_launches, bool bits_ready,
-                 const cudaGraphConditionalHandle *cond)
+                 const cudaGraphConditionalHandle *cond, int nest_ctas)
 {
     int n = 0;
     const dim3 pgrid((W + 127) / 128, (H + 7) / 8, n_streams);
@@ -1416,7 +1413,7 @@ int launch_blobs(const BlobBuffers &B, ImageU8 mask, int H, int W, int n_streams
         n++;
     }
     GOFPID_TRY(launch_labelling(mask, B.bitimg, B.bit_pitch, B.bit_stream, B.runs, B.labels, B.labels_pitch,
-                                B.labels_stream, B.comp, B.max_blobs, H, W, n_streams, B.info, tick, 0, s, cond));
+                                B.labels_stream, B.comp, B.max_blobs, H, W, n_streams, B.info, tick, 0, s, cond, B.runs_cap));
     if (cond) {
         // `s` is being captured: the fallback kernels go into the body of an IF node whose condition
         // runs_ccl_kernel raises, so a normal frame does not even launch them
@@ -1458,7 +1455,7 @@ int launch_blobs(const BlobBuffers &B, ImageU8 mask, int H, int W, int n_streams
         B.labels, B.labels_pitch, B.labels_stream, B.runs, B.comp, B.info, B.kept, B.points, B.max_blobs,
         B.max_kept, B.max_points, B.area_min, B.bitimg, B.bit_pitch, B.bit_stream, H, W);
     GOFPID_CUDA_TRY(cudaGetLastError());
-    nest_kernel<<<n_streams, 256, 0, s>>>(B.info, B.kept, B.points, B.max_kept, B.max_points, W);
+    nest_kernel<<<dim3(nest_ctas > 0 ? nest_ctas : 1, n_streams), 256, 0, s>>>(B.info, B.kept, B.points, B.max_kept, B.max_points, W);
     GOFPID_CUDA_TRY(cudaGetLastError());
     if (n_launches) *n_launches = n + (B.runs.max_runs > 0 ? 4 : 3);
     return GOFPID_OK;
@@ -1508,8 +1505,11 @@ int launch_ccl_only(const uint8_t *d_mask, size_t mask_pitch, int32_t *d_labels,
     const int bit_pitch = (int)round_up((size_t)(W + 31) / 32 + 2, 4);
     const size_t bit_words = (size_t)bit_pitch * (H + 2);
     const int max_blobs = 1 << 16;
+    // (stage-level test entry point: its two knobs are read per call, it is not on the pipeline's path)
     const char *e = getenv("GOFPID_CCL_FORCE_TILED");
     const int force = e && e[0] == '1';
+    const char *rc_e = getenv("GOFPID_RUNS_CAP");
+    const int runs_cap = rc_e && atoi(rc_e) >= 0 ? atoi(rc_e) : -1;
     uint8_t *pm = nullptr;
     int32_t *pl = nullptr, *comp = nullptr, *slot = nullptr;
     uint32_t *bits = nullptr;
@@ -1531,7 +1531,7 @@ int launch_ccl_only(const uint8_t *d_mask, size_t mask_pitch, int32_t *d_labels,
         }
         ImageU8 m{pm, MP, 0};
         pack_bits_kernel<<<dim3((W + 127) / 128, (H + 7) / 8, 1), dim3(32, 8), 0, s>>>(m, bits, bit_pitch, 0, H, W);
-        rc = launch_labelling(m, bits, bit_pitch, 0, R, pl, LP, 0, comp, max_blobs, H, W, 1, fi, nullptr, force, s, nullptr);
+        rc = launch_labelling(m, bits, bit_pitch, 0, R, pl, LP, 0, comp, max_blobs, H, W, 1, fi, nullptr, force, s, nullptr, runs_cap);
         if (rc) break;
         rc = launch_tiled_labelling(m, pl, LP, 0, H, W, 1, fi, 0, s);
         if (rc) break;

@@ -33,6 +33,21 @@ void set_error(const char *fmt, ...);
 
 static inline size_t round_up(size_t v, size_t m) { return (v + m - 1) / m * m; }
 
+// Experiment / test knobs (GOFPID_* environment variables), read ONCE per handle in
+// gofpid_pipeline_create -- never on the per-frame path.
+struct Tuning {
+    int depth = 0;        // GOFPID_DEPTH: frame slots (0: default)
+    int group = 0;        // GOFPID_MOG2_GROUP: frames per MOG2 launch in the clip entry points (0: default)
+    int b_prio_low = 0;   // GOFPID_B_PRIO=0: stage-B streams at the lowest priority
+    int no_graph = 0;     // GOFPID_NO_GRAPH=1: eager launches only
+    int no_cond = 0;      // GOFPID_NO_COND=1: tiled fallback launched unconditionally (ncu cannot profile conditional nodes)
+    int morph_bytes = 0;  // GOFPID_MORPH_BYTES=1: byte morphology kernel inside the pipeline
+    int knn_scalar = 0;   // GOFPID_KNN_SCALAR=1: general KNN kernel on gray frames too (tests)
+    int runs_cap = -1;    // GOFPID_RUNS_CAP: run capacity of the shared-memory labeller (tests: force the fallback)
+    int event_timing = 0; // GOFPID_EVENT_TIMING=1: slot events keep timestamps (debug build tools)
+};
+Tuning read_tuning();
+
 // ------------------------------------------------------------------ geometry
 // Fused blur+detect kernels: a CTA owns a tile of (32*PX) x DET_TH pixels; thread (tx, ty)
 // owns PX consecutive pixels of one row.
@@ -192,7 +207,7 @@ void mog2_prepare_lr(const Mog2Params &mp, long n_done, float (*lr)[4]); // rate
 const void *mog2_kernel_func(int C, int H, int W);
 void mog2_kernel_params(Mog2Args &a, void **params); // params[9]
 int launch_knn(const DetectLaunch &L, KnnModel model, const KnnParams &kp,
-               const uint64_t *d_jump_table);
+               const uint64_t *d_jump_table, bool force_scalar = false);
 int detect_launches_per_step(int detector);
 
 // morphology ------------------------------------------------------------------
@@ -261,11 +276,12 @@ struct BlobBuffers {
     int32_t *points;      // per stream: max_points * 2 int32
     int max_blobs, max_kept, max_points;
     double area_min;
+    int runs_cap;         // < 0: the run list's own capacity (Tuning::runs_cap)
 };
 // bits_ready: the morphology kernel already wrote B.bitimg for this mask
 int launch_blobs(const BlobBuffers &B, ImageU8 mask, int H, int W, int n_streams,
                  const FrameTick *tick, cudaStream_t s, int *n_launches, bool bits_ready,
-                 const cudaGraphConditionalHandle *cond = nullptr);
+                 const cudaGraphConditionalHandle *cond = nullptr, int nest_ctas = 1);
 // h_*: device-side addresses of the pinned host mirrors (cudaHostGetDevicePointer)
 int launch_results_to_host(const BlobBuffers &B, gofpid_frame_info *h_info, gofpid_blob *h_kept, int32_t *h_points,
                            int n_streams, cudaStream_t s);

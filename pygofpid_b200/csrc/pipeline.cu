@@ -26,6 +26,28 @@ void set_error(const char *fmt, ...)
     va_end(ap);
 }
 
+Tuning read_tuning()
+{
+    Tuning t;
+    auto num = [](const char *name, int lo, int hi, int dflt) {
+        const char *e = getenv(name);
+        if (!e || !e[0]) return dflt;
+        const int v = atoi(e);
+        return v >= lo && v <= hi ? v : dflt;
+    };
+    auto flag = [](const char *name, char on) { const char *e = getenv(name); return e && e[0] == on ? 1 : 0; };
+    t.depth = num("GOFPID_DEPTH", 1, 16, 0);
+    t.group = num("GOFPID_MOG2_GROUP", 1, MOG2_MAX_GROUP, 0);
+    t.b_prio_low = flag("GOFPID_B_PRIO", '0');
+    t.no_graph = flag("GOFPID_NO_GRAPH", '1');
+    t.no_cond = flag("GOFPID_NO_COND", '1');
+    t.morph_bytes = flag("GOFPID_MORPH_BYTES", '1');
+    t.knn_scalar = flag("GOFPID_KNN_SCALAR", '1');
+    t.runs_cap = num("GOFPID_RUNS_CAP", 0, 1 << 30, -1);
+    t.event_timing = flag("GOFPID_EVENT_TIMING", '1');
+    return t;
+}
+
 } // namespace gofpid
 
 using namespace gofpid;
@@ -76,6 +98,7 @@ struct FrameSlot {
 
 struct gofpid_pipeline {
     gofpid_config cfg;
+    Tuning tune; // GOFPID_* knobs as they were when the handle was created
     std::vector<std::vector<uint8_t>> se_copies;
     int H = 0, W = 0, C = 0, n_streams = 0, device = 0; // C: channels the kernels work on
     int Csrc = 0;                                        // channels of the frames (3 with a gray conversion)
@@ -113,6 +136,18 @@ struct gofpid_pipeline {
     const uint8_t *pinned_lo = nullptr, *pinned_hi = nullptr; // host range last found to be page-locked
     uint8_t *h_frames = nullptr; // pinned staging for pageable input
     uint8_t *d_frames_base = nullptr; // device staging of all slots (slot i at i * frames_stream * n_streams)
+
+    // a frame that exceeded the slot capacities, re-run with buffers of the size it needs (rerun_big)
+    struct {
+        const FrameSlot *slot = nullptr;
+        int frame_index = -1, stream = -1;
+        gofpid_frame_info info = {};
+        std::vector<gofpid_blob> kept;
+        std::vector<int32_t> points;
+    } big;
+    // blob lists of the last clip call when the caller's buffers were too small (gofpid_pipeline_sequence_results)
+    std::vector<gofpid_blob> seq_blobs;
+    std::vector<int32_t> seq_points;
 
     bool profiling = false;
     cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -258,18 +293,17 @@ int build(gofpid_pipeline *p)
         const bool mog2 = cfg.detector == GOFPID_DETECT_MOG2;
         if (mog2) p->depth = p->n_streams <= 8 ? DEFAULT_DEPTH_MOG2 : DEFAULT_DEPTH_MOG2_MANY;
         else p->depth = p->n_streams <= 8 ? DEFAULT_DEPTH : DEFAULT_DEPTH_MANY;
-        const char *e = getenv("GOFPID_DEPTH");
-        if (e && atoi(e) >= 1 && atoi(e) <= MAX_DEPTH) p->depth = atoi(e);
+        if (cfg.depth >= 1 && cfg.depth <= MAX_DEPTH) p->depth = cfg.depth;
+        if (p->tune.depth >= 1 && p->tune.depth <= MAX_DEPTH) p->depth = p->tune.depth;
         p->group = mog2 ? DEFAULT_GROUP : 1;
-        const char *ge = getenv("GOFPID_MOG2_GROUP");
-        if (mog2 && ge && atoi(ge) >= 1 && atoi(ge) <= MOG2_MAX_GROUP) p->group = atoi(ge);
+        if (mog2 && cfg.mog2_group >= 1 && cfg.mog2_group <= MOG2_MAX_GROUP) p->group = cfg.mog2_group;
+        if (mog2 && p->tune.group >= 1) p->group = p->tune.group;
         p->group = std::max(1, std::min(p->group, p->depth / 2));
         // stage B runs at a higher priority than stage A: its few CTAs take the SMs they need as soon
         // as the detector's CTAs drain instead of queueing behind the whole grid
         int lo = 0, hi = 0;
         GOFPID_CUDA_TRY(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-        const char *pe = getenv("GOFPID_B_PRIO");
-        const int prio = (pe && pe[0] == '0') ? lo : hi;
+        const int prio = p->tune.b_prio_low ? lo : hi;
         for (int i = 0; i < p->depth; i++)
             GOFPID_CUDA_TRY(cudaStreamCreateWithPriority(&p->stream_b[i], cudaStreamNonBlocking, prio));
     }
@@ -344,10 +378,7 @@ int build(gofpid_pipeline *p)
     p->tick_args.knn_u_table = p->d_knn_table; p->tick_args.knn_table_len = p->knn_table_len;
     p->tick_args.pow2tab = p->d_pow2tab; p->tick_args.total = H * W; p->tick_args.n_streams = S;
     p->tick_args.src = FrameSrc{nullptr, 0, 0};
-    {
-        const char *e = getenv("GOFPID_NO_GRAPH");
-        p->use_graph = !(e && e[0] == '1');
-    }
+    p->use_graph = !p->tune.no_graph;
 
     GOFPID_TRY(morph_plan_create(p->cfg.morph, p->cfg.n_morph, &p->morph));
     {
@@ -361,8 +392,7 @@ int build(gofpid_pipeline *p)
             if (cfg.detect_shadows && sv > 0 && sv < 255) lv[n++] = sv;
             lv[n++] = 255;
         }
-        const char *e = getenv("GOFPID_MORPH_BYTES");
-        if (!(e && e[0] == '1')) morph_plan_set_levels(&p->morph, lv, n);
+        if (!p->tune.morph_bytes) morph_plan_set_levels(&p->morph, lv, n);
     }
 
     if (cfg.find_blobs) {
@@ -377,8 +407,7 @@ int build(gofpid_pipeline *p)
         FrameSlot &F = p->slots[si];
         GOFPID_TRY(alloc_zero((void **)&F.d_final, p->mask_stream * S));
         if (cfg.n_morph > 0) GOFPID_TRY(alloc_zero((void **)&F.d_mask_det, p->mask_stream * S));
-        const char *et = getenv("GOFPID_EVENT_TIMING"); // (tools/timeline_debug.py: when does each slot's stage end)
-        const unsigned evf = (et && et[0] == '1') ? cudaEventDefault : cudaEventDisableTiming;
+        const unsigned evf = p->tune.event_timing ? cudaEventDefault : cudaEventDisableTiming; // (tools/timeline_debug.py)
         GOFPID_CUDA_TRY(cudaEventCreateWithFlags(&F.ev_mask, evf));
         GOFPID_CUDA_TRY(cudaEventCreateWithFlags(&F.ev_blobs, evf));
         GOFPID_CUDA_TRY(cudaEventCreateWithFlags(&F.ev_h2d, cudaEventDisableTiming));
@@ -388,6 +417,7 @@ int build(gofpid_pipeline *p)
         BlobBuffers &B = F.blobs;
         B.max_blobs = cfg.max_blobs; B.max_kept = cfg.max_kept; B.max_points = cfg.max_points;
         B.area_min = cfg.blob_area_min;
+        B.runs_cap = p->tune.runs_cap;
         B.labels_pitch = round_up((size_t)W, 4);
         B.labels_stream = B.labels_pitch * H;
         GOFPID_TRY(alloc_zero((void **)&B.labels, B.labels_stream * sizeof(int32_t) * S));
@@ -437,7 +467,7 @@ int enqueue_stage_a(gofpid_pipeline *p, FrameSlot &F, const FrameSrc &src, cudaS
         one.aligned4 = mog2_group_aligned4(one, src);
         F.mog2_args = Mog2Args{L.blur, L.mask, p->mog2, p->mog2p, p->d_tick, src, one, p->H, p->W};
     }
-    else if (p->cfg.detector == GOFPID_DETECT_KNN) GOFPID_TRY(launch_knn(L, p->knn, p->knnp, p->d_pow2tab));
+    else if (p->cfg.detector == GOFPID_DETECT_KNN) GOFPID_TRY(launch_knn(L, p->knn, p->knnp, p->d_pow2tab, p->tune.knn_scalar != 0));
     else GOFPID_TRY(launch_fd(L, p->fd, p->fd_thr));
     launches += detect_launches_per_step(p->cfg.detector);
     if (prof) GOFPID_CUDA_TRY(cudaEventRecord(p->ev[1], s));
@@ -502,8 +532,7 @@ int build_graphs(gofpid_pipeline *p, FrameSlot &F, const FrameSrc &src)
     if (!F.tick_node) { set_error("graph capture: frame-source node not found"); return GOFPID_ERR_CUDA; }
     GOFPID_CUDA_TRY(cudaGraphInstantiate(&F.exec_a, F.graph_a, 0));
     if (p->cfg.find_blobs || p->cfg.n_morph > 0) {
-        const char *nc = getenv("GOFPID_NO_COND");
-        const bool use_cond = p->cfg.find_blobs && !(nc && nc[0] == '1');
+        const bool use_cond = p->cfg.find_blobs && !p->tune.no_cond;
         GOFPID_CUDA_TRY(cudaGraphCreate(&F.graph_b, 0));
         if (use_cond)
             GOFPID_CUDA_TRY(cudaGraphConditionalHandleCreate(&F.cond_b, F.graph_b, 0, cudaGraphCondAssignDefault));
@@ -594,7 +623,7 @@ int run_step(gofpid_pipeline *p, const uint8_t *d_frames, size_t pitch, size_t s
     p->launches_total += la + lb;
     F.used = true;
     F.fetched = false;
-    F.frame_index = (int)(++p->frames);
+    F.frame_index = (int)std::min<long>(++p->frames, 0x7fffffffL);
     p->selected = 0;
     return GOFPID_OK;
 }
@@ -646,7 +675,7 @@ int run_group(gofpid_pipeline *p, const uint8_t *const *frames, int g, size_t pi
             GOFPID_CUDA_TRY(cudaEventRecord(F.ev_blobs, s));
             F.used = true;
             F.fetched = false;
-            F.frame_index = (int)(++p->frames);
+            F.frame_index = (int)std::min<long>(++p->frames, 0x7fffffffL);
         }
         GOFPID_CUDA_TRY(cudaEventRecord(p->ev[3], s));
         p->launch_count = 1 + lb;
@@ -669,7 +698,7 @@ int run_group(gofpid_pipeline *p, const uint8_t *const *frames, int g, size_t pi
         }
         F.used = true;
         F.fetched = false;
-        F.frame_index = (int)(++p->frames);
+        F.frame_index = (int)std::min<long>(++p->frames, 0x7fffffffL);
     }
     const int lbg = p->from_host && slot[0]->exec_b2 ? p->launches_b2 : p->launches_b;
     p->launch_count = 1 + lbg; // (kernels of the newest frame: its share of the group launch + stage B)
@@ -693,6 +722,155 @@ int fetch_results(gofpid_pipeline *p, FrameSlot *F)
     // headers, records and points arrived with the step (results_to_host_kernel, enqueue_stage_b)
     for (int z = 0; z < S; z++) F->h_info[z].frame_index = F->frame_index;
     F->fetched = true;
+    return GOFPID_OK;
+}
+
+// A frame that exceeded the handle's per-slot blob capacities (noise without morphology, an illumination
+// step, a fractal outline ...) is not an error for the reference, so it is not one here: blob creation
+// runs once more on the slot's still-resident final mask (and bit image) with buffers of the size the
+// frame needs -- the overflowed pass counted the components, the next one counts kept blobs and contour
+// points exactly -- while the temporal model is untouched.  Rare and synchronous.
+int rerun_big(gofpid_pipeline *p, FrameSlot *F, int z)
+{
+    if (p->big.slot == F && p->big.frame_index == F->frame_index && p->big.stream == z) return GOFPID_OK;
+    p->big.slot = nullptr;
+    const int H = p->H, W = p->W;
+    const gofpid_frame_info first = F->h_info[z];
+    BlobBuffers B = F->blobs; // the slot's run list, label / slot images and bit image, stream z only
+    B.labels += (size_t)z * B.labels_stream;
+    B.slot += (size_t)z * B.labels_pitch * H;
+    B.bitimg += (size_t)z * B.bit_stream;
+    {
+        RunList &R = B.runs;
+        const size_t mr = (size_t)(R.max_runs ? R.max_runs : 8);
+        R.xs += z * mr; R.xe += z * mr; R.y += z * mr; R.label += z * mr; R.byc += z * mr;
+        R.rowstart += (size_t)z * R.row_pitch; R.rowend += (size_t)z * R.row_pitch;
+        R.count += z; R.n_labelled += z;
+    }
+    const ImageU8 mask{F->d_final + (size_t)z * p->mask_stream, p->mask_pitch, p->mask_stream};
+    const long worst_comp = (long)((H + 1) / 2) * ((W + 1) / 2);
+    long need_blobs = std::max<long>(first.n_components, B.max_blobs);
+    long need_kept = std::max<long>(2L * first.n_kept, B.max_kept);
+    long need_points = std::max<long>(2L * first.n_points, 4L * B.max_points);
+    cudaStream_t s = p->stream_c;
+    int rc = GOFPID_OK;
+    for (int pass = 0; pass < 4; pass++) {
+        need_blobs = std::min(need_blobs, worst_comp);
+        need_kept = std::min(need_kept, need_blobs);
+        need_points = std::min<long>(need_points, 0x3fffffffL);
+        B.max_blobs = (int)need_blobs; B.max_kept = (int)need_kept; B.max_points = (int)need_points;
+        B.comp = nullptr; B.kept = nullptr; B.points = nullptr; B.info = nullptr;
+        gofpid_frame_info fi;
+        memset(&fi, 0, sizeof(fi));
+        if (cudaMalloc(&B.comp, (size_t)B.max_blobs * 8 * sizeof(int32_t)) != cudaSuccess ||
+            cudaMalloc(&B.kept, (size_t)B.max_kept * sizeof(gofpid_blob)) != cudaSuccess ||
+            cudaMalloc(&B.points, (size_t)B.max_points * 2 * sizeof(int32_t)) != cudaSuccess ||
+            cudaMalloc(&B.info, sizeof(gofpid_frame_info)) != cudaSuccess) {
+            cudaGetLastError();
+            set_error("out of device memory re-running a frame with %ld components / %ld blobs / %ld contour points",
+                      need_blobs, need_kept, need_points);
+            rc = GOFPID_ERR_NOMEM;
+        }
+        if (rc == GOFPID_OK && cudaMemsetAsync(B.info, 0, sizeof(gofpid_frame_info), s) != cudaSuccess) rc = GOFPID_ERR_CUDA;
+        int nl = 0;
+        if (rc == GOFPID_OK) rc = launch_blobs(B, mask, H, W, 1, nullptr, s, &nl, true, nullptr, 64);
+        if (rc == GOFPID_OK && (cudaMemcpyAsync(&fi, B.info, sizeof(fi), cudaMemcpyDeviceToHost, s) != cudaSuccess ||
+                                cudaStreamSynchronize(s) != cudaSuccess)) {
+            set_error("re-running blob creation failed: %s", cudaGetErrorString(cudaGetLastError()));
+            rc = GOFPID_ERR_CUDA;
+        }
+        p->launches_total += nl;
+        const bool fits = rc == GOFPID_OK && (fi.overflow & 7) == 0;
+        if (fits) {
+            const int nk = std::min(fi.n_kept, B.max_kept), np = std::min(fi.n_points, B.max_points);
+            p->big.kept.resize((size_t)std::max(nk, 1));
+            p->big.points.resize((size_t)std::max(np, 1) * 2);
+            if ((nk && cudaMemcpy(p->big.kept.data(), B.kept, (size_t)nk * sizeof(gofpid_blob), cudaMemcpyDeviceToHost) != cudaSuccess) ||
+                (np && cudaMemcpy(p->big.points.data(), B.points, (size_t)np * 2 * sizeof(int32_t), cudaMemcpyDeviceToHost) != cudaSuccess)) {
+                set_error("fetching the re-run blob lists failed: %s", cudaGetErrorString(cudaGetLastError()));
+                rc = GOFPID_ERR_CUDA;
+            }
+            fi.frame_index = F->frame_index;
+            p->big.info = fi;
+        }
+        cudaFree(B.comp); cudaFree(B.kept); cudaFree(B.points); cudaFree(B.info);
+        if (rc != GOFPID_OK) return rc;
+        if (fits) {
+            p->big.slot = F; p->big.frame_index = F->frame_index; p->big.stream = z;
+            return GOFPID_OK;
+        }
+        // what the pass counted is exact for whatever fitted before it; grow and go again
+        if (fi.overflow & 1) need_blobs = std::max<long>(fi.n_components, 2 * need_blobs);
+        if (fi.overflow & 2) need_kept = std::max<long>(fi.n_kept, 2 * need_kept);
+        if (fi.overflow & 4) need_points = std::max<long>(fi.n_points, 2 * need_points);
+        if (fi.overflow & 1) { need_kept = std::max(need_kept, need_blobs / 8); need_points = std::max(need_points, 4 * need_points); }
+    }
+    set_error("blob creation did not fit after four passes (components %ld, blobs %ld, points %ld)", need_blobs, need_kept, need_points);
+    return GOFPID_ERR_OVERFLOW;
+}
+
+// Where the selected frame's blob records and contour points of stream z are (the slot's pinned mirrors,
+// or the re-run's vectors for a frame that exceeded the slot capacities).
+struct BlobView {
+    gofpid_frame_info fi;
+    const gofpid_blob *kb;
+    const int32_t *pts;
+    int nk;
+};
+int blob_view(gofpid_pipeline *p, FrameSlot *F, int z, BlobView *v)
+{
+    GOFPID_TRY(fetch_results(p, F));
+    const BlobBuffers &B = F->blobs;
+    v->fi = F->h_info[z];
+    if (v->fi.overflow & 8) {
+        set_error("internal error: a border did not close (frame %d, stream %d)", F->frame_index, z);
+        return GOFPID_ERR_OVERFLOW;
+    }
+    if (v->fi.overflow) {
+        GOFPID_TRY(rerun_big(p, F, z));
+        v->fi = p->big.info;
+        v->kb = p->big.kept.data();
+        v->pts = p->big.points.data();
+        v->nk = p->big.info.n_kept;
+        return GOFPID_OK;
+    }
+    v->nk = std::min(v->fi.n_kept, B.max_kept);
+    v->kb = F->h_kept + (size_t)z * B.max_kept;
+    v->pts = F->h_points + (size_t)z * B.max_points * 2;
+    return GOFPID_OK;
+}
+
+// Blobs of the selected frame in the reference's order (descending raster order of each component's
+// first pixel; blobs enclosed by another blob were flagged on the device: RETR_EXTERNAL drops them).
+// n_blobs / n_points always receive the sizes; GOFPID_ERR_INVALID when they exceed the capacities.
+int ordered_blobs(gofpid_pipeline *p, FrameSlot *F, int z, gofpid_blob *h_blobs, int blob_capacity, int32_t *h_points,
+                  int point_capacity, int *n_blobs, int *n_points)
+{
+    BlobView v;
+    GOFPID_TRY(blob_view(p, F, z, &v));
+    std::vector<int> order;
+    order.reserve(v.nk);
+    for (int i = 0; i < v.nk; i++)
+        if (!v.kb[i].nested) order.push_back(i);
+    std::sort(order.begin(), order.end(), [&](int a, int b) { return v.kb[a].first > v.kb[b].first; });
+    const int nout = (int)order.size();
+    long total = 0;
+    for (int i = 0; i < nout; i++) total += v.kb[order[i]].n_points;
+    if (n_blobs) *n_blobs = nout;
+    if (n_points) *n_points = (int)total;
+    if (!h_blobs && !h_points) return GOFPID_OK; // size query
+    if (nout > blob_capacity || total > point_capacity) {
+        set_error("output capacity too small: need %d blobs, %ld points", nout, total);
+        return GOFPID_ERR_INVALID;
+    }
+    int off = 0;
+    for (int i = 0; i < nout; i++) {
+        gofpid_blob b = v.kb[order[i]];
+        if (h_points) memcpy(h_points + (size_t)off * 2, v.pts + (size_t)b.point_offset * 2, sizeof(int32_t) * 2 * b.n_points);
+        b.point_offset = off;
+        off += b.n_points;
+        if (h_blobs) h_blobs[i] = b;
+    }
     return GOFPID_OK;
 }
 
@@ -812,23 +990,45 @@ int run_sequence(gofpid_pipeline *p, const uint8_t *frames, bool host, int n_fra
                  int32_t *h_points, int point_capacity, int32_t *h_counts)
 {
     const int S = p->n_streams;
-    int nb_total = 0, np_total = 0;
+    long nb_total = 0, np_total = 0;
     int t = 0, c = 0; // frames of this clip submitted / collected
+    // Blob lists go straight into the caller's buffers while they fit.  From the first frame that does
+    // not, everything moves to vectors of the handle: the clip still runs to its end (the temporal
+    // model and h_counts are complete), the call reports the sizes, and the caller fetches the lists
+    // with gofpid_pipeline_sequence_results.
+    bool spilled = false;
+    p->seq_blobs.clear(); p->seq_points.clear();
     auto collect = [&](int upto) -> int { // every frame of the clip up to `upto` (inclusive)
         for (; c <= upto; c++) {
-            p->selected = t - 1 - c;
+            FrameSlot *F = &p->slots[(p->frames - (t - c)) % p->depth];
             for (int z = 0; z < S; z++) {
                 int nb = 0, np = 0;
-                const int rc = gofpid_pipeline_blobs(p, z, h_blobs ? h_blobs + nb_total : nullptr, blob_capacity - nb_total,
-                                                     h_points ? h_points + (size_t)np_total * 2 : nullptr,
-                                                     point_capacity - np_total, &nb, &np);
-                if (rc != GOFPID_OK) { p->selected = 0; return rc; }
+                int rc = GOFPID_OK;
+                if ((h_blobs || h_points) && !spilled) {
+                    rc = ordered_blobs(p, F, z, h_blobs ? h_blobs + nb_total : nullptr, (int)(blob_capacity - nb_total),
+                                       h_points ? h_points + (size_t)np_total * 2 : nullptr,
+                                       (int)(point_capacity - np_total), &nb, &np);
+                    if (rc == GOFPID_ERR_INVALID && (nb > blob_capacity - nb_total || np > point_capacity - np_total)) {
+                        spilled = true;
+                        if (h_blobs) p->seq_blobs.assign(h_blobs, h_blobs + nb_total);
+                        if (h_points) p->seq_points.assign(h_points, h_points + (size_t)np_total * 2);
+                    }
+                } else if (!spilled) {
+                    rc = ordered_blobs(p, F, z, nullptr, 0, nullptr, 0, &nb, &np); // counts only
+                }
+                if (spilled) {
+                    GOFPID_TRY(ordered_blobs(p, F, z, nullptr, 0, nullptr, 0, &nb, &np));
+                    p->seq_blobs.resize((size_t)nb_total + nb);
+                    p->seq_points.resize(((size_t)np_total + np) * 2);
+                    rc = ordered_blobs(p, F, z, p->seq_blobs.data() + nb_total, nb, p->seq_points.data() + (size_t)np_total * 2, np,
+                                       &nb, &np);
+                }
+                if (rc != GOFPID_OK) return rc;
                 h_counts[((size_t)c * S + z) * 2] = nb;
                 h_counts[((size_t)c * S + z) * 2 + 1] = np;
                 if (h_blobs || h_points) { nb_total += nb; np_total += np; }
             }
         }
-        p->selected = 0;
         return GOFPID_OK;
     };
     while (t < n_frames) {
@@ -848,6 +1048,11 @@ int run_sequence(gofpid_pipeline *p, const uint8_t *frames, bool host, int n_fra
         t += g;
     }
     if (h_counts) GOFPID_TRY(collect(n_frames - 1));
+    if (spilled) {
+        set_error("output capacity too small: the clip needs %ld blobs, %ld points (the lists are kept: "
+                  "gofpid_pipeline_sequence_results)", nb_total, np_total);
+        return GOFPID_ERR_INVALID;
+    }
     return GOFPID_OK;
 }
 
@@ -900,6 +1105,25 @@ GOFPID_API void gofpid_config_default(gofpid_config *cfg)
     cfg->max_points = 0; // 0: sized from the frame (see gofpid_pipeline_create)
 }
 
+GOFPID_API int gofpid_host_alloc(size_t bytes, int write_combined, void **out)
+{
+    if (!out) { set_error("null output"); return GOFPID_ERR_INVALID; }
+    *out = nullptr;
+    if (gofpid_device_count() == 0) { set_error("no CUDA device available (no CPU fallback)"); return GOFPID_ERR_CUDA; }
+    const unsigned flags = cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0u);
+    if (cudaHostAlloc(out, bytes ? bytes : 1, flags) != cudaSuccess) {
+        cudaGetLastError();
+        set_error("cannot page-lock %zu bytes of host memory", bytes);
+        return GOFPID_ERR_NOMEM;
+    }
+    return GOFPID_OK;
+}
+GOFPID_API int gofpid_host_free(void *ptr)
+{
+    if (ptr && cudaFreeHost(ptr) != cudaSuccess) { cudaGetLastError(); set_error("not a gofpid_host_alloc pointer"); return GOFPID_ERR_INVALID; }
+    return GOFPID_OK;
+}
+
 GOFPID_API int gofpid_gaussian_taps_q8(int n, double sigma, uint16_t *h_taps)
 {
     if (!h_taps) { set_error("null output"); return GOFPID_ERR_INVALID; }
@@ -938,6 +1162,7 @@ GOFPID_API int gofpid_pipeline_create(const gofpid_config *cfg, int H, int W, in
     gofpid_pipeline *p = new (std::nothrow) gofpid_pipeline();
     if (!p) { set_error("out of host memory"); return GOFPID_ERR_NOMEM; }
     p->cfg = *cfg;
+    p->tune = read_tuning();
     if (p->cfg.max_points <= 0) { // contour points per frame: 32 frame perimeters' worth, 64 Ki .. 1 Mi
         const long want = 32L * (H + W);
         p->cfg.max_points = (int)(want < 65536 ? 65536 : (want > (1L << 20) ? (1L << 20) : want));
@@ -1048,8 +1273,10 @@ GOFPID_API int gofpid_pipeline_process_device_sequence(gofpid_pipeline *p, const
                         blob_capacity, h_points, point_capacity, h_counts);
 }
 
-// Debug aids (not part of the ABI in include/): a mark on `stream`, then per slot the milliseconds
-// from the mark to the end of the slot's stage A and stage B (needs GOFPID_EVENT_TIMING=1).
+#ifdef GOFPID_TRACE_DEBUG
+// Debug aids of the instrumented build only (make debug; not part of the ABI in include/): a mark on
+// `stream`, then per slot the milliseconds from the mark to the end of the slot's stage A and stage B
+// (needs GOFPID_EVENT_TIMING=1).
 GOFPID_API int gofpid_debug_mark(gofpid_pipeline *p, void *stream)
 {
     GOFPID_GUARD(p);
@@ -1068,6 +1295,15 @@ GOFPID_API int gofpid_debug_slot_times(gofpid_pipeline *p, float *ms2, int *fram
         if (cudaEventElapsedTime(&ms2[2 * i], p->ev[5], F.ev_mask) != cudaSuccess) cudaGetLastError();
         if (cudaEventElapsedTime(&ms2[2 * i + 1], p->ev[5], F.ev_blobs) != cudaSuccess) cudaGetLastError();
     }
+    return GOFPID_OK;
+}
+#endif
+
+GOFPID_API int gofpid_pipeline_join(gofpid_pipeline *p, void *stream)
+{
+    GOFPID_GUARD(p);
+    for (int i = 0; i < p->depth; i++)
+        if (p->slots[i].used) GOFPID_CUDA_TRY(cudaStreamWaitEvent((cudaStream_t)stream, p->slots[i].ev_blobs, 0));
     return GOFPID_OK;
 }
 
@@ -1117,42 +1353,21 @@ GOFPID_API int gofpid_pipeline_blobs(gofpid_pipeline *p, int stream_idx, gofpid_
     GOFPID_TRY(check_stream_index(p, stream_idx));
     if (!p->cfg.find_blobs) { set_error("pipeline was created with find_blobs = 0"); return GOFPID_ERR_INVALID; }
     FrameSlot *F = selected_slot(p);
-    GOFPID_TRY(fetch_results(p, F));
-    const BlobBuffers &B = F->blobs;
-    const gofpid_frame_info &fi = F->h_info[stream_idx];
-    const int nk = std::min(fi.n_kept, B.max_kept);
-    const gofpid_blob *kb = F->h_kept + (size_t)stream_idx * B.max_kept;
-    const int32_t *pts = F->h_points + (size_t)stream_idx * B.max_points * 2;
-    // the reference's order: descending raster order of each component's first pixel
-    // (blobs enclosed by another blob were flagged on the device: RETR_EXTERNAL drops them)
-    std::vector<int> order;
-    order.reserve(nk);
-    for (int i = 0; i < nk; i++)
-        if (!kb[i].nested) order.push_back(i);
-    std::sort(order.begin(), order.end(), [&](int a, int b) { return kb[a].first > kb[b].first; });
-    const int nout = (int)order.size();
-    int total = 0;
-    for (int i = 0; i < nout; i++) total += kb[order[i]].n_points;
-    if (n_blobs) *n_blobs = nout;
-    if (n_points) *n_points = total;
-    if (fi.overflow) {
-        set_error("blob capacity exceeded (flags %d): components %d/%d, kept %d/%d, points %d/%d",
-                  fi.overflow, fi.n_components, B.max_blobs, fi.n_kept, B.max_kept, fi.n_points, B.max_points);
-        return GOFPID_ERR_OVERFLOW;
-    }
-    if (!h_blobs && !h_points) return GOFPID_OK; // size query
-    if (nout > blob_capacity || total > point_capacity) {
-        set_error("output capacity too small: need %d blobs, %d points", nout, total);
+    if (!F) { set_error("no frame has been processed yet"); return GOFPID_ERR_INVALID; }
+    return ordered_blobs(p, F, stream_idx, h_blobs, blob_capacity, h_points, point_capacity, n_blobs, n_points);
+}
+
+GOFPID_API int gofpid_pipeline_sequence_results(gofpid_pipeline *p, gofpid_blob *h_blobs, int blob_capacity,
+                                                int32_t *h_points, int point_capacity)
+{
+    GOFPID_GUARD(p);
+    const size_t nb = p->seq_blobs.size(), np = p->seq_points.size() / 2;
+    if ((h_blobs && nb > (size_t)std::max(blob_capacity, 0)) || (h_points && np > (size_t)std::max(point_capacity, 0))) {
+        set_error("output capacity too small: need %zu blobs, %zu points", nb, np);
         return GOFPID_ERR_INVALID;
     }
-    int off = 0;
-    for (int i = 0; i < nout; i++) {
-        gofpid_blob b = kb[order[i]];
-        if (h_points) memcpy(h_points + (size_t)off * 2, pts + (size_t)b.point_offset * 2, sizeof(int32_t) * 2 * b.n_points);
-        b.point_offset = off;
-        off += b.n_points;
-        if (h_blobs) h_blobs[i] = b;
-    }
+    if (h_blobs && nb) memcpy(h_blobs, p->seq_blobs.data(), nb * sizeof(gofpid_blob));
+    if (h_points && np) memcpy(h_points, p->seq_points.data(), np * 2 * sizeof(int32_t));
     return GOFPID_OK;
 }
 

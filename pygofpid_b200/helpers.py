@@ -5,16 +5,16 @@ behaviour) so that code written against the reference keeps working; the impleme
 independent NumPy code and do not need OpenCV.  Blob creation itself runs on the GPU
 (`find_contours` drives the CUDA labelling + border tracing of libgofpid_b200).
 """
+import threading
+
 import numpy as np
 
 
 # ------------------------------------------------------------------------------ files
 def change_extension(filename_input, ext_new="png"):
-    """`name.ext` -> `name.<ext_new>` (reference: helpers.py:7-10)."""
-    stem, _, _old = filename_input.rpartition('.')
-    if not stem:
-        return filename_input + '.' + ext_new
-    return filename_input.replace(_old, ext_new)
+    """Replaces what follows the last dot -- every occurrence of it, and the whole name when there is
+    no dot -- by `ext_new`, exactly as the reference does (helpers.py:7-10)."""
+    return filename_input.replace(filename_input.split('.')[-1], ext_new)
 
 
 def read_first_frame(video_filename):
@@ -121,29 +121,35 @@ def get_center(contour, dtype=np.int16):
 
 
 _contour_engines = {}
+_contour_lock = threading.Lock()
 
 
-def find_contours(mask):
+def find_contours(mask, device=0):
     """Outer contours of the 8-connected components of `mask` that are not enclosed by another
     component -- cv.findContours(mask, RETR_EXTERNAL, CHAIN_APPROX_NONE) (helpers.py:125-150) --
-    computed on the GPU (labelling + border tracing of libgofpid_b200)."""
+    computed on the GPU `device` (labelling + border tracing of libgofpid_b200).  One engine per
+    (shape, device) is kept and shared under a lock."""
     from .hotpath import HotPath
     mask = np.ascontiguousarray(mask)
     if mask.ndim == 3 and mask.shape[2] == 1:
         mask = mask[..., 0]
     if mask.ndim != 2 or mask.dtype != np.uint8:
         raise ValueError("mask must be a 2-D uint8 array")
-    hp = _contour_engines.get(mask.shape)
-    if hp is None:
-        # |mask - 0| > 0 turns the mask into its own foreground mask; area_min <= 0 keeps all
-        hp = HotPath(mask.shape, blur=None, detector="FD", morph=(), fd_threshold=0, area_min=-1.0)
-        _contour_engines.clear()
-        _contour_engines[mask.shape] = hp
-    hp.reset()
-    hp.process(np.zeros_like(mask))
-    hp.process(mask)
-    recs, pts = hp.raw_blobs()
-    return tuple(pts[b.point_offset:b.point_offset + b.n_points].reshape(-1, 1, 2).copy() for b in recs)
+    key = (mask.shape, int(device))
+    with _contour_lock:
+        hp = _contour_engines.get(key)
+        if hp is None:
+            # |mask - 0| > 0 turns the mask into its own foreground mask; area_min <= 0 keeps all
+            # (one synchronous frame at a time: two slots are enough)
+            hp = HotPath(mask.shape, blur=None, detector="FD", morph=(), fd_threshold=0, area_min=-1.0,
+                         device=device, depth=2)
+            _contour_engines.clear()
+            _contour_engines[key] = hp
+        hp.reset()
+        hp.process(np.zeros_like(mask))
+        hp.process(mask)
+        recs, pts = hp.raw_blobs()
+        return tuple(pts[b.point_offset:b.point_offset + b.n_points].reshape(-1, 1, 2).copy() for b in recs)
 
 
 # ------------------------------------------------------------------------------ coordinates
@@ -200,26 +206,3 @@ class SimpleLinearRegression():
 
     def predict_clip(self, x, a_min=None, a_max=None):
         return np.clip(self.predict(x), a_min=a_min, a_max=a_max)
-
-
-# ------------------------------------------------------------------------------ drawing (display only)
-def plot_squares(X, points, thickness, c=(0, 0, 255)):
-    import cv2 as cv
-    for point in points:
-        cv.rectangle(X, point - thickness, point + thickness, c, -1)
-
-
-def plot_lines(X, points, thickness, c=(0, 0, 255)):
-    import cv2 as cv
-    n = len(points)
-    if n >= 2:
-        for i in range(n):
-            cv.line(X, points[i % n], points[(i + 1) % n], c, 2)
-    plot_squares(X, points, thickness, c=c)
-
-
-def plot_rectangles(X, points, thickness, c=(0, 0, 255)):
-    import cv2 as cv
-    cv.rectangle(X, points[0], points[1], c, 2)
-    cv.rectangle(X, points[2], points[3], c, 2)
-    plot_squares(X, points, thickness, c=c)

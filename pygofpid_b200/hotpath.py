@@ -34,6 +34,30 @@ def gaussian_taps_q8(n, sigma):
     return np.array(q[:int(n)], dtype=np.uint16)
 
 
+class PinnedFrames:
+    """Page-locked (optionally write-combined) host memory for frames, as a numpy uint8 array
+    (gofpid_host_alloc): `PinnedFrames(shape).array[...] = clip`, then hand `.array` to
+    process_sequence / submit_pinned.  Freed with the object."""
+
+    def __init__(self, shape, write_combined=False):
+        n = int(np.prod(shape))
+        self._p = ct.c_void_p()
+        nat.check(nat.lib().gofpid_host_alloc(n, 1 if write_combined else 0, ct.byref(self._p)))
+        self.array = np.ctypeslib.as_array(ct.cast(self._p, ct.POINTER(ct.c_uint8)), shape=(n,)).reshape(shape)
+
+    def close(self):
+        p, self._p = getattr(self, "_p", None), None
+        if p:
+            self.array = None
+            nat.lib().gofpid_host_free(p)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
 # numpy view of gofpid_blob (include/gofpid_b200.h)
 BLOB_DTYPE = np.dtype([(n, '<i4') for n in ('first', 'x0', 'y0', 'x1', 'y1', 'area_px', 'n_points', 'point_offset',
                                               'nested', 'reserved')] + [(n, '<i8') for n in ('a00', 'a10', 'a01')])
@@ -59,9 +83,14 @@ class HotPath:
     def __init__(self, shape, blur=("gaussian", (3, 3), 4.0), detector="MOG2", morph=(),
                  area_min=100.0, n_streams=1, device=0, find_blobs=True, fd_threshold=5,
                  knn_seed=0, max_blobs=1 << 16, max_kept=4096, max_points=0,
-                 detect_shadows=True, convert=None):
+                 detect_shadows=True, convert=None, depth=0, mog2_group=0):
         """convert: None | 'bgr2gray' | 'rgb2gray' -- frames are (H, W, 3) and the path works on their
-        gray value (cv.cvtColor of pipeline.py:458-459, computed while the frame is loaded)."""
+        gray value (cv.cvtColor of pipeline.py:458-459, computed while the frame is loaded).
+        max_blobs / max_kept / max_points: per-frame capacities of the pipelined path (components,
+        kept blobs, contour points; 0 points: sized from the frame); a frame beyond them is re-run with
+        larger buffers when its blobs are fetched, never refused.
+        depth: frame slots (frames in flight; 0: default), mog2_group: frames per MOG2 launch in the
+        clip entry points (0: default)."""
         L = nat.lib()
         if len(shape) == 2:
             H, W, C = int(shape[0]), int(shape[1]), 1
@@ -107,6 +136,7 @@ class HotPath:
         cfg.blob_area_min = float(area_min)
         cfg.max_blobs, cfg.max_kept, cfg.max_points = int(max_blobs), int(max_kept), int(max_points)
         cfg.convert = {None: 0, "bgr2gray": 1, "rgb2gray": 2}[convert]
+        cfg.depth, cfg.mog2_group = int(depth), int(mog2_group)
         # self.C: channels of the frames the caller passes (3 with a gray conversion)
         self.H, self.W, self.C, self.n_streams, self.device = H, W, C, int(n_streams), int(device)
         self.Cm = 1 if convert else C  # channels of the model / state
@@ -161,7 +191,7 @@ class HotPath:
 
     def submit_pinned(self, ptr, pitch, stream_stride):
         """Asynchronous process_pinned(): enqueue the H2D copy and the step, return at once.
-        Up to three frames are in flight; collect results with select(age) + the getters."""
+        Up to `depth` frames are in flight; collect results with select(age) + the getters."""
         nat.check(self._L.gofpid_pipeline_submit_host(self._h, ptr, pitch, stream_stride))
 
     @property
@@ -251,9 +281,9 @@ class HotPath:
             raise ValueError("Input shape has changed.")
         T = shape[0]
         row = self.W * self.C
-        # default capacities: 256 blobs and 8 (H + W) contour points per frame and stream (what travels
-        # to the host with every step); a clip that needs more raises ValueError -- the temporal model
-        # has advanced by then, so size generously or reset()
+        # default capacities: 256 blobs and 8 (H + W) contour points per frame and stream; a clip that
+        # needs more still runs to its end inside the library, which keeps the lists and reports the
+        # sizes -- they are fetched below with gofpid_pipeline_sequence_results
         bc = int(blob_capacity or 256 * T * self.n_streams)
         pc = int(point_capacity or max(4096, 8 * (self.H + self.W)) * T * self.n_streams)
         counts = np.zeros((T, self.n_streams, 2), np.int32)
@@ -271,10 +301,14 @@ class HotPath:
                 self._h, ptr, T, row * self.H * self.n_streams, row, row * self.H,
                 recs.ctypes.data_as(ct.POINTER(nat.Blob)), bc, pts.ctypes.data_as(ct.POINTER(ct.c_int32)), pc,
                 counts.ctypes.data_as(ct.POINTER(ct.c_int32)))
-        if rc == nat.ERR_INVALID and "capacity" in nat.last_error():
-            raise ValueError("blob_capacity / point_capacity too small for this clip: " + nat.last_error())
-        nat.check(rc)
         nb, npt = int(counts[..., 0].sum()), int(counts[..., 1].sum())
+        if rc == nat.ERR_INVALID and "gofpid_pipeline_sequence_results" in nat.last_error():
+            recs = np.empty(max(nb, 1), BLOB_DTYPE)
+            pts = np.empty((max(npt, 1), 2), np.int32)
+            rc = self._L.gofpid_pipeline_sequence_results(
+                self._h, recs.ctypes.data_as(ct.POINTER(nat.Blob)), len(recs),
+                pts.ctypes.data_as(ct.POINTER(ct.c_int32)), len(pts))
+        nat.check(rc)
         return counts, recs[:nb], pts[:npt]
 
     def enqueue_device_sequence(self, ptr, n_frames, frame_stride, pitch, stream_stride, cuda_stream=0):
@@ -283,6 +317,11 @@ class HotPath:
         nat.check(self._L.gofpid_pipeline_process_device_sequence(
             self._h, ptr, int(n_frames), int(frame_stride), int(pitch), int(stream_stride), cuda_stream,
             None, 0, None, 0, None))
+
+    def join(self, cuda_stream=0):
+        """Orders `cuda_stream` after everything enqueued so far, stage B on the internal streams
+        included (gofpid_pipeline_join); does not block the host."""
+        nat.check(self._L.gofpid_pipeline_join(self._h, cuda_stream))
 
     @property
     def group(self):

@@ -24,8 +24,7 @@ import math
 
 import numpy as np
 
-from .helpers import (SimpleLinearRegression, normalize_coords, point_in_polygon, read_first_frame,
-                      unnormalize_coords)
+from .helpers import SimpleLinearRegression, point_in_polygon, unnormalize_coords
 from .segmentation import ViBe
 
 try:  # OpenCV is only needed for the parameter objects users pass in, and for display()
@@ -92,6 +91,13 @@ class GOFPID():
     knn_seed : int, default=0
         State of the cv::RNG replica KNN draws from (0 = OpenCV's default state); the
         reference consumes the calling thread's cv.theRNG() instead.
+    max_blobs, max_kept, max_points : int
+        Per-frame capacities of the GPU path (connected components, blobs that pass the area filter,
+        contour points; 0 points = sized from the frame).  A frame that exceeds them is not refused:
+        its blobs are created again with larger buffers (slower for that frame).
+    depth : int, default=0
+        Frame slots of the GPU pipeline (0 = default: deep, for `detect_clip`); `detect` alone never
+        has more than one frame in flight and works with depth=2 (saves device memory).
 
     Attributes
     ----------
@@ -113,6 +119,10 @@ class GOFPID():
         verbose=False,
         device=0,
         knn_seed=0,
+        max_blobs=1 << 16,
+        max_kept=4096,
+        max_points=0,
+        depth=0,
     ):
         self.convert = convert
         self.blur = blur
@@ -124,6 +134,10 @@ class GOFPID():
         self.verbose = verbose
         self.device = device
         self.knn_seed = knn_seed
+        self.max_blobs = max_blobs
+        self.max_kept = max_kept
+        self.max_points = max_points
+        self.depth = depth
 
     # ------------------------------------------------------------------ configuration
     def initialize(self):
@@ -232,44 +246,22 @@ class GOFPID():
         if pf.get('display_config'):
             pf['perspective'] = self._config_perspective()
 
-    # interactive configuration windows (reference pipeline.py:308-432) need an OpenCV GUI build
-    def _get_config_img(self):
-        pf = self.post_filter
-        if 'config_video_filename' in pf.keys():
-            img = read_first_frame(pf['config_video_filename'])
-        elif 'config_frame_filename' in pf.keys():
-            img = cv.imread(pf['config_frame_filename'])
-        elif 'config_frame' in pf.keys():
-            img = pf['config_frame']
-        else:
-            if self.verbose:
-                print("No configuration video or frame defined.")
-            img = 100 * np.ones((240, 320, 3), dtype=np.uint8)
-        if img is None:
-            raise ValueError('Configuration image is None.')
-        thickness = unnormalize_coords(np.array([[0.02, 0.02]]), img.shape, dtype=np.int32)[0]
-        return img, img.copy(), thickness
-
     def _config_perimeter(self, window_name="Configure perimeter"):
-        from .gui import configure_perimeter
-        perimeter = configure_perimeter(self, window_name)
-        if self.verbose:
-            print("Config perimeter:\n", perimeter)
-        return perimeter
+        raise NotImplementedError("interactive configuration windows (reference pipeline.py:308-407) are "
+                                  "outside the hot path: pass 'perimeter' as an array")
 
     def _config_perspective(self, window_name="Configure perspective"):
-        from .gui import configure_perspective
-        perspective = configure_perspective(self, window_name)
-        if self.verbose:
-            print("Config perspective:\n", perspective)
-        return perspective
+        raise NotImplementedError("interactive configuration windows (reference pipeline.py:308-407) are "
+                                  "outside the hot path: pass 'perspective' as an array")
 
     # ------------------------------------------------------------------ per frame
     @property
     def foreground_mask_(self):
         """Foreground mask of the last frame, (H, W) uint8 (reference pipeline.py:476);
         copied from the GPU on first access after each `detect`."""
-        if self._mask_cache is None and self._engine is not None:
+        if self._mask_cache is None:
+            if getattr(self, '_engine', None) is None:  # the reference sets the attribute in detect()
+                raise AttributeError("'GOFPID' object has no attribute 'foreground_mask_'")
             self._mask_cache = self._engine.mask()
         return self._mask_cache
 
@@ -363,7 +355,9 @@ class GOFPID():
         if len(shape) == 3 and shape[2] == 1:
             shape = shape[:2]
         return HotPath(shape, blur=blur, detector=detector, morph=morph, area_min=100.0,
-                       device=self.device, knn_seed=self.knn_seed, convert=convert)
+                       device=self.device, knn_seed=self.knn_seed, convert=convert,
+                       max_blobs=self.max_blobs, max_kept=self.max_kept, max_points=self.max_points,
+                       depth=self.depth)
 
     def _hot_path(self, X, convert=None):
         if self._engine is None:

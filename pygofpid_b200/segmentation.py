@@ -26,8 +26,9 @@ class FrameDifferencing(ForegroundEstimator):
     The first frame gives an all-background mask; 3-channel frames give per-channel masks
     averaged in uint8 arithmetic exactly as the reference's `np.mean(..., dtype=np.uint8)`."""
 
-    def __init__(self, threshold=5):
+    def __init__(self, threshold=5, device=0):
         self.threshold = threshold
+        self.device = device
         self._engine = None
         self._shape = None
 
@@ -37,7 +38,7 @@ class FrameDifferencing(ForegroundEstimator):
         if self._engine is None or X.shape != self._shape:
             shape = X.shape[:2] if (X.ndim == 3 and X.shape[2] == 1) else X.shape
             self._engine = HotPath(shape, blur=None, detector="FD", morph=(), find_blobs=False,
-                                   fd_threshold=self.threshold)
+                                   fd_threshold=self.threshold, device=self.device, depth=2)
             self._shape = X.shape
         self._engine.process(X)
         return self._engine.mask()

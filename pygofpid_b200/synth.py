@@ -10,8 +10,13 @@ import numpy as np
 
 class SyntheticClip:
     def __init__(self, H, W, C=1, seed=0, n_obj=6, noise_sigma=4.0, obj_size=None, shadow_band=True,
-                 obj_gain=70.0):
+                 obj_gain=70.0, rng="legacy"):
+        """rng='legacy': all randomness from one RandomState stream, frames in order (the parity tests
+        and the golden vectors).  rng='pcg': the noise of frame t comes from its own
+        np.random.default_rng([seed, t]) in float32 -- several times faster and frames can be
+        produced in any order / in parallel (`frame_at`); what bench.py uses for its large clips."""
         self.H, self.W, self.C = int(H), int(W), int(C)
+        self.seed, self.rng = int(seed), rng
         self.rs = np.random.RandomState(seed)
         yy, xx = np.mgrid[0:H, 0:W]
         bg = 96.0 + 48.0 * np.sin(xx / 37.0) + 32.0 * np.cos(yy / 23.0)
@@ -34,15 +39,24 @@ class SyntheticClip:
         self.t = 0
 
     def next(self):
-        f = self.bg + self.rs.standard_normal(self.bg.shape).astype(np.float32) * self.noise_sigma
-        t = self.t
+        f = self.frame_at(self.t)
+        self.t += 1
+        return f
+
+    def frame_at(self, t):
+        if self.rng == "pcg":
+            noise = np.random.default_rng([self.seed, int(t)]).standard_normal(self.bg.shape, dtype=np.float32)
+        elif t != self.t:
+            raise ValueError("rng='legacy' produces frames in order only")
+        else:
+            noise = self.rs.standard_normal(self.bg.shape).astype(np.float32)
+        f = self.bg + noise * self.noise_sigma
         for (x, y, w, h, vx, vy) in self.objs:
             x0, y0 = (x + vx * t) % self.W, (y + vy * t) % self.H
             f[y0:y0 + h, x0:x0 + w] += self.obj_gain
         if self.shadow_band:
             b0 = (3 * t) % self.W
             f[:, b0:b0 + max(4, self.W // 64)] *= 0.7
-        self.t += 1
         return np.clip(f, 0, 255).astype(np.uint8)
 
     def frames(self, n):

@@ -72,3 +72,101 @@ def test_ilids_720x576_bgr_defaults_matches_cv2():
     se = cv.getStructuringElement(cv.MORPH_RECT, (5, 5))
     _run(576, 720, 3, "MOG2", [dict(fun=cv.erode, kernel=se), dict(fun=cv.dilate, kernel=se)],
          [("erode", se), ("dilate", se)], n_frames=30, seed=1000, n_obj=6)
+
+
+# ----------------------------------------------------------------------------------------------
+# The BENCHMARKED entry points at the benchmarked shapes: clips through
+# gofpid_pipeline_process_host_sequence / _device_sequence with G frames per MOG2 launch -- whole
+# 64x8 tiles at 1920x1080 and 3840x2160, so this is mog2_kernel<1, FULL=true> carried through frame
+# groups with the next frame's words prefetched in registers -- against live cv2: EVERY frame's mask
+# and blob list, and the final model planes against the C restatement of MOG2.
+def _run_clip(H, W, morph_cv, morph_hp, G, via, n_chunks, seed, n_obj, C=1):
+    import torch
+    from oracle import cport
+    from pygofpid_b200 import HotPath
+    from pygofpid_b200.hotpath import blobs_from_records
+    depth = 16 if G == 8 else 12
+    hp = HotPath((H, W) if C == 1 else (H, W, C), blur=("gaussian", (3, 3), 4.0), detector="MOG2", morph=morph_hp,
+                 area_min=100.0, depth=depth, mog2_group=G)
+    assert hp.group == G and hp.depth == depth
+    ref = cv_path.CvHotPath(frg_detect="MOG2", mat_morph=morph_cv)
+    ora = cport.MOG2(H, W, C)
+    clip = SyntheticClip(H, W, C, seed=seed, n_obj=n_obj)
+    L = depth - depth % G  # frames per clip call: whole groups, all still selectable afterwards
+    t0 = 0
+    for chunk in range(n_chunks):
+        frames = np.stack(clip.frames(L))
+        want = [ref.step(f) for f in frames]
+        for f in frames:
+            ora.apply(ref.blurred(f))
+        src = torch.from_numpy(frames).cuda() if via == "device" else (
+            torch.from_numpy(frames).pin_memory() if via == "pinned" else frames)
+        counts, recs, pts = hp.process_sequence(src)
+        ob = op = 0
+        for t in range(L):
+            nb, npt = int(counts[t, 0, 0]), int(counts[t, 0, 1])
+            got = blobs_from_records(recs[ob:ob + nb], pts[op:op + npt])
+            ob += nb; op += npt
+            wm, wb = want[t]
+            assert len(got) == len(wb), (t0 + t, len(got), len(wb))
+            for g, w in zip(got, wb):
+                assert np.array_equal(g["contour"], w["contour"]), t0 + t
+                assert np.array_equal(g["center"], w["center"]) and np.array_equal(g["bottom"], w["bottom"]), t0 + t
+            hp.select(L - 1 - t)
+            gm = hp.mask()
+            assert np.array_equal(gm, wm), (t0 + t, int((gm != wm).sum()))
+        hp.select(0)
+        t0 += L
+    w, v, m, k = hp.mog2_model()
+    ow, ov, om, ok = ora.planes()
+    assert np.array_equal(k, ok)
+    live = np.arange(5)[None, None, :] < ok[..., None]
+    assert np.array_equal(w[live], ow[live]) and np.array_equal(v[live], ov[live]) and np.array_equal(m[live], om[live])
+    hp.close()
+    return t0
+
+
+@pytest.mark.parametrize("G,via", [(3, "device"), (3, "pinned"), (8, "device"), (8, "host")])
+def test_1080p_headline_clip_entry_points_match_cv2(G, via):
+    se = cv.getStructuringElement(cv.MORPH_RECT, (5, 5))
+    chain = [cv.erode, cv.dilate, cv.dilate, cv.erode]
+    n = _run_clip(1080, 1920, [dict(fun=f, kernel=se) for f in chain],
+                  [("erode" if f is cv.erode else "dilate", se) for f in chain], G, via, n_chunks=4, seed=2, n_obj=12)
+    assert n >= 40
+
+
+@pytest.mark.parametrize("G,via", [(3, "device"), (8, "pinned")])
+def test_4k_clip_entry_points_match_cv2(G, via):
+    se = cv.getStructuringElement(cv.MORPH_ELLIPSE, (15, 15))
+    n = _run_clip(2160, 3840, [dict(fun=cv.erode, kernel=se), dict(fun=cv.dilate, kernel=se)],
+                  [("erode", se), ("dilate", se)], G, via, n_chunks=3, seed=3, n_obj=16)
+    assert n >= 36
+
+
+def test_1080p_bgr_clip_entry_point_matches_cv2():
+    se = cv.getStructuringElement(cv.MORPH_RECT, (5, 5))
+    _run_clip(1080, 1920, [dict(fun=cv.erode, kernel=se), dict(fun=cv.dilate, kernel=se)],
+              [("erode", se), ("dilate", se)], 3, "device", n_chunks=2, seed=2, n_obj=12, C=3)
+
+
+def test_1080p_noise_without_morphology_through_the_dropin():
+    """a noisy sensor with mat_morph=None at 1080p -- tens of thousands of components per
+    frame, far beyond the per-slot capacities -- must give the reference's blob list, not an exception."""
+    from pygofpid_b200 import GOFPID
+    rs = np.random.RandomState(11)
+    H, W = 1080, 1920
+    g = GOFPID(frg_detect='FD', mat_morph=None, blur=None).initialize()
+    ref = cv_path.CvHotPath(blur=None, frg_detect="FD", mat_morph=None)
+    base = rs.randint(0, 256, (H, W)).astype(np.uint8)
+    for t in range(4):
+        f = base.copy()
+        flip = rs.rand(H, W) < (0.30 if t != 2 else 0.45)  # t == 2: beyond the 8-connected percolation threshold
+        f[flip] = f[flip] + 100  # wraps: |f - prev| is mostly > 5 where flipped
+        wm, wb = ref.step(f)
+        g.detect(f)
+        assert np.array_equal(g.foreground_mask_, wm)
+        assert len(g.blobs_) == len(wb), (t, len(g.blobs_), len(wb))
+        for a, b in zip(g.blobs_, wb):
+            assert np.array_equal(a["contour"], b["contour"]), t
+            assert np.array_equal(a["center"], b["center"]) and np.array_equal(a["bottom"], b["bottom"]), t
+        base = f
