@@ -44,6 +44,7 @@ struct Tuning {
     int morph_bytes = 0;  // GOFPID_MORPH_BYTES=1: byte morphology kernel inside the pipeline
     int knn_scalar = 0;   // GOFPID_KNN_SCALAR=1: general KNN kernel on gray frames too (tests)
     int runs_cap = -1;    // GOFPID_RUNS_CAP: run capacity of the shared-memory labeller (tests: force the fallback)
+    int mog2_generic = 0; // GOFPID_MOG2_GENERIC=1: the generic MOG2 kernel even for ordinary parameters (tests)
     int event_timing = 0; // GOFPID_EVENT_TIMING=1: slot events keep timestamps (debug build tools)
 };
 Tuning read_tuning();
@@ -77,6 +78,7 @@ struct BlurParams {
     uint32_t cw[3];
     // 3x3 kernels whose taps fit a byte: the taps packed for dp4a (0: not available)
     uint32_t qx3, qy3;
+    uint32_t q3x[3], q3y[3]; // ... and one per word (operands straight from the constant bank)
 };
 int make_blur_params(int kind, int kw, int kh, double sigma, BlurParams *bp);
 int gaussian_taps_q8(int n, double sigma, uint16_t *q);
@@ -121,6 +123,7 @@ struct Mog2Params {
     float Tb, TB, Tg, varInit, varMin, varMax, tau;
     int detectShadows, shadowVal, history;
     float ct;
+    int force_generic; // Tuning::mog2_generic: never take the lean kernel
 };
 // MOG2 model, tiled: per stream tiles_x * tiles_y tiles of MOG2_TILE_W x MOG2_TILE_H pixels; a
 // tile is one contiguous block [mode][plane: weight, var, mean c..][512 px] of floats, so its
@@ -204,7 +207,7 @@ struct Mog2Args {
 int launch_mog2(const DetectLaunch &L, Mog2Model model, const Mog2Params &mp, FrameTick *tick,
                 const Mog2Group *grp = nullptr);
 void mog2_prepare_lr(const Mog2Params &mp, long n_done, float (*lr)[4]); // rates of frames n_done+1 ..
-const void *mog2_kernel_func(int C, int H, int W);
+const void *mog2_kernel_func(int C, int H, int W, const Mog2Params &mp);
 void mog2_kernel_params(Mog2Args &a, void **params); // params[9]
 int launch_knn(const DetectLaunch &L, KnnModel model, const KnnParams &kp,
                const uint64_t *d_jump_table, bool force_scalar = false);

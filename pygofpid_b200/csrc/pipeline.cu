@@ -45,6 +45,7 @@ Tuning read_tuning()
     t.knn_scalar = flag("GOFPID_KNN_SCALAR", '1');
     t.runs_cap = num("GOFPID_RUNS_CAP", 0, 1 << 30, -1);
     t.event_timing = flag("GOFPID_EVENT_TIMING", '1');
+    t.mog2_generic = flag("GOFPID_MOG2_GENERIC", '1');
     return t;
 }
 
@@ -329,6 +330,7 @@ int build(gofpid_pipeline *p)
     mp.varInit = cfg.mog2_var_init; mp.varMin = cfg.mog2_var_min; mp.varMax = cfg.mog2_var_max;
     mp.tau = cfg.shadow_tau; mp.detectShadows = cfg.detect_shadows; mp.shadowVal = cfg.shadow_value;
     mp.history = cfg.mog2_history; mp.ct = cfg.mog2_ct;
+    mp.force_generic = p->tune.mog2_generic;
     KnnParams &kp = p->knnp;
     kp.Tb = cfg.knn_dist2_threshold; kp.tau = cfg.shadow_tau; kp.knn = cfg.knn_k;
     kp.detectShadows = cfg.detect_shadows; kp.shadowVal = cfg.shadow_value; kp.history = cfg.knn_history;
@@ -526,7 +528,7 @@ int build_graphs(gofpid_pipeline *p, FrameSlot &F, const FrameSrc &src)
         if (t != cudaGraphNodeTypeKernel) continue;
         cudaKernelNodeParams kp;
         GOFPID_CUDA_TRY(cudaGraphKernelNodeGetParams(nodes[i], &kp));
-        const void *want = p->cfg.detector == GOFPID_DETECT_MOG2 ? mog2_kernel_func(p->C, p->H, p->W) : tick_kernel_func();
+        const void *want = p->cfg.detector == GOFPID_DETECT_MOG2 ? mog2_kernel_func(p->C, p->H, p->W, p->mog2p) : tick_kernel_func();
         if (kp.func == want) { F.tick_node = nodes[i]; F.src_node_params = kp; break; }
     }
     if (!F.tick_node) { set_error("graph capture: frame-source node not found"); return GOFPID_ERR_CUDA; }

@@ -50,9 +50,14 @@ def test_fd_masks_and_state(H, W, C, blur):
 
 
 # ----------------------------------------------------------------------------- MOG2
+@pytest.mark.parametrize("generic", [False, True])
 @pytest.mark.parametrize("H,W,C,sigma", [(48, 64, 1, 6), (48, 64, 3, 6), (37, 53, 1, 25), (37, 53, 3, 25),
                                           (120, 200, 1, 4)])
-def test_mog2_masks_and_model_bitexact(H, W, C, sigma):
+def test_mog2_masks_and_model_bitexact(H, W, C, sigma, generic, monkeypatch):
+    """Both MOG2 kernels against the oracle: the lean one (ordinary parameters: the default) and the generic
+    one (GOFPID_MOG2_GENERIC=1 keeps it for ordinary parameters too)."""
+    if generic:
+        monkeypatch.setenv("GOFPID_MOG2_GENERIC", "1")
     hp = _hot(_shape(H, W, C), blur=None, detector="MOG2", morph=(), find_blobs=False)
     ora = cport.MOG2(H, W, C)
     clip = SyntheticClip(H, W, C, seed=10 * C + sigma, n_obj=4, noise_sigma=sigma)
@@ -358,7 +363,9 @@ def test_sequence_call_equals_frame_by_frame_calls():
 
 @pytest.mark.parametrize("group", [1, 2, 3, 4, 8])
 @pytest.mark.parametrize("H,W,C,sigma,blur", [(40, 260, 1, 6, ("gaussian", (3, 3), 4.0)), (37, 53, 3, 25, None),
-                                              (41, 331, 1, 25, ("box", (3, 3))), (24, 200, 3, 6, ("gaussian", (5, 5), 4.0))])
+                                              (41, 331, 1, 25, ("box", (3, 3))), (24, 200, 3, 6, ("gaussian", (5, 5), 4.0)),
+                                              (48, 320, 1, 25, ("gaussian", (3, 3), 4.0)), (32, 192, 3, 6, ("gaussian", (3, 3), 4.0)),
+                                              (48, 320, 1, 25, "generic")])
 def test_mog2_frame_groups_bitexact(group, H, W, C, sigma, blur, monkeypatch):
     """Temporal blocking: the clip entry point carries every tile through `group` frames per MOG2
     launch (modes resident in shared memory).  Masks of EVERY frame and the model state stay
@@ -366,6 +373,9 @@ def test_mog2_frame_groups_bitexact(group, H, W, C, sigma, blur, monkeypatch):
     import torch
     monkeypatch.setenv("GOFPID_MOG2_GROUP", str(group))
     monkeypatch.setenv("GOFPID_DEPTH", "16")
+    if blur == "generic":  # whole tiles (48 x 320: the FULL instantiation, interior tiles) on the generic kernel
+        monkeypatch.setenv("GOFPID_MOG2_GENERIC", "1")
+        blur = ("gaussian", (3, 3), 4.0)
     hp = _hot(_shape(H, W, C), blur=blur, detector="MOG2", morph=(), find_blobs=False)
     assert hp.group == group and hp.depth == 16
     ora = cport.MOG2(H, W, C)
