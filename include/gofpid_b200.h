@@ -291,6 +291,61 @@ GOFPID_API int gofpid_pipeline_launch_count(gofpid_pipeline *p);
 /* Number of kernels launched since creation / the last reset (all entry points). */
 GOFPID_API int gofpid_pipeline_launch_total(gofpid_pipeline *p, long long *n_launches);
 
+/* ---- host tail: blob tracking, post-filtering, alarm (GOFPID.detect steps 5-7) ---------------
+ * Replaces pipeline.py:590-799 (_track_blob .. _maintain_alarm) for one camera stream.  Pure host code,
+ * no CUDA call: usable without a device.  The arithmetic keeps the reference's data types (int16 centres
+ * whose differences and squares wrap, int32 ellipse radii, float64 quotients). */
+typedef struct gofpid_tracker gofpid_tracker; /* opaque */
+typedef struct gofpid_tracker_config {
+    int32_t H;                    /* frame rows = length of the two perspective tables                     */
+    const double *persp_height;   /* GOFPID._perspective['height'] (pipeline.py:509-547), H values          */
+    const double *persp_area;     /* GOFPID._perspective['area'],   H values                                */
+    const int32_t *perimeter;     /* post_filter['perimeter'] in pixels: n_perimeter (x, y) pairs           */
+    int32_t n_perimeter;
+    double tracking_factor;       /* tracking['factor']                                                     */
+    int32_t absence_max;          /* tracking['absence_max']                                                */
+    int32_t anchor_center;        /* post_filter['anchor'] == 'center' (else 'bottom')                      */
+    double perspective_coeff, presence_min, distance_min; /* post_filter                                    */
+    int32_t keep_alarm;           /* alarm_def                                                              */
+    double duration_min;
+} gofpid_tracker_config;
+/* One tracked blob (an entry of the reference's tracked_blobs_, pipeline.py:630-645). */
+#define GOFPID_FILTER_PRESENCE 1
+#define GOFPID_FILTER_DISTANCE 2
+#define GOFPID_FILTER_PERIMETER 4
+#define GOFPID_FILTER_PERSPECTIVE 8
+typedef struct gofpid_track {
+    int16_t anchor[2], bottom[2], center[2], center_first[2];
+    int32_t presence, absence;
+    int32_t filtered;             /* GOFPID_FILTER_* bits: the reference's set of filter names            */
+    int32_t already_in_alarm;
+    int32_t x0, y0, x1, y1;       /* cv.boundingRect of the contour (inclusive corners)                     */
+    int32_t n_points;             /* contour length (gofpid_tracker_contour)                                */
+} gofpid_track;
+GOFPID_API int gofpid_tracker_create(const gofpid_tracker_config *cfg, gofpid_tracker **out);
+GOFPID_API int gofpid_tracker_destroy(gofpid_tracker *t);
+GOFPID_API int gofpid_tracker_reset(gofpid_tracker *t);
+/* Steps 5-7 for one frame from the blob records of gofpid_pipeline_blobs / a clip call (centre and bottom
+ * are formed from the Green sums as GOFPID._create_blob does); *alarm = what GOFPID.detect returns. */
+GOFPID_API int gofpid_tracker_step(gofpid_tracker *t, const gofpid_blob *h_blobs, int n_blobs,
+                                   const int32_t *h_points, int *alarm);
+/* The same for blobs given as the reference's blob dictionaries hold them: anchor / bottom / center as
+ * n_blobs (x, y) int16 pairs, h_boxes = (x0, y0, x1, y1) int32 per blob, contour i = points
+ * h_offsets[i] .. h_offsets[i + 1] of h_points. */
+GOFPID_API int gofpid_tracker_step_prepared(gofpid_tracker *t, int n_blobs, const int16_t *h_anchor,
+                                            const int16_t *h_bottom, const int16_t *h_center,
+                                            const int32_t *h_boxes, const int32_t *h_points,
+                                            const int32_t *h_offsets, int *alarm);
+/* A whole clip: the outputs of gofpid_pipeline_process_host_sequence / _device_sequence (h_counts: blob and
+ * point count per frame and stream) for camera stream `stream_idx`; h_alarms receives one byte per frame. */
+GOFPID_API int gofpid_tracker_run(gofpid_tracker *t, const gofpid_blob *h_blobs, const int32_t *h_points,
+                                  const int32_t *h_counts, int n_frames, int n_streams, int stream_idx,
+                                  uint8_t *h_alarms);
+GOFPID_API int gofpid_tracker_count(gofpid_tracker *t);
+GOFPID_API int gofpid_tracker_get(gofpid_tracker *t, int i, gofpid_track *out);
+GOFPID_API int gofpid_tracker_contour(gofpid_tracker *t, int i, int32_t *h_points, int point_capacity);
+GOFPID_API int gofpid_tracker_alarm_state(gofpid_tracker *t, int *already_in_alarm, double *duration);
+
 /* ---- stage-level entry points (device buffers, used by the parity tests) ------------- */
 /* cv.GaussianBlur / cv.blur on u8, BORDER_REFLECT_101 (pipeline.py:463). */
 GOFPID_API int gofpid_blur_u8(const uint8_t *d_src, size_t src_pitch, uint8_t *d_dst,

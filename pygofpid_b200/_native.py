@@ -67,6 +67,21 @@ class FrameInfo(ct.Structure):
                 ("reserved", ct.c_int32 * 2)]
 
 
+class TrackerConfig(ct.Structure):
+    _fields_ = [("H", ct.c_int32), ("persp_height", ct.POINTER(ct.c_double)), ("persp_area", ct.POINTER(ct.c_double)),
+                ("perimeter", ct.POINTER(ct.c_int32)), ("n_perimeter", ct.c_int32),
+                ("tracking_factor", ct.c_double), ("absence_max", ct.c_int32), ("anchor_center", ct.c_int32),
+                ("perspective_coeff", ct.c_double), ("presence_min", ct.c_double), ("distance_min", ct.c_double),
+                ("keep_alarm", ct.c_int32), ("duration_min", ct.c_double)]
+
+
+class Track(ct.Structure):
+    _fields_ = [("anchor", ct.c_int16 * 2), ("bottom", ct.c_int16 * 2), ("center", ct.c_int16 * 2),
+                ("center_first", ct.c_int16 * 2), ("presence", ct.c_int32), ("absence", ct.c_int32),
+                ("filtered", ct.c_int32), ("already_in_alarm", ct.c_int32),
+                ("x0", ct.c_int32), ("y0", ct.c_int32), ("x1", ct.c_int32), ("y1", ct.c_int32), ("n_points", ct.c_int32)]
+
+
 # name -> (restype, argtypes); must list every GOFPID_API symbol of include/gofpid_b200.h
 _u8p = ct.POINTER(ct.c_uint8)
 _i32p = ct.POINTER(ct.c_int32)
@@ -113,6 +128,16 @@ SIGNATURES = {
     "gofpid_pipeline_stage_ms": (ct.c_int, [_vp, _f32p]),
     "gofpid_pipeline_launch_count": (ct.c_int, [_vp]),
     "gofpid_pipeline_launch_total": (ct.c_int, [_vp, ct.POINTER(ct.c_longlong)]),
+    "gofpid_tracker_create": (ct.c_int, [ct.POINTER(TrackerConfig), ct.POINTER(_vp)]),
+    "gofpid_tracker_destroy": (ct.c_int, [_vp]),
+    "gofpid_tracker_reset": (ct.c_int, [_vp]),
+    "gofpid_tracker_step": (ct.c_int, [_vp, _vp, ct.c_int, _vp, ct.POINTER(ct.c_int)]),
+    "gofpid_tracker_step_prepared": (ct.c_int, [_vp, ct.c_int, _vp, _vp, _vp, _vp, _vp, _vp, ct.POINTER(ct.c_int)]),
+    "gofpid_tracker_run": (ct.c_int, [_vp, _vp, _vp, _vp, ct.c_int, ct.c_int, ct.c_int, _vp]),
+    "gofpid_tracker_count": (ct.c_int, [_vp]),
+    "gofpid_tracker_get": (ct.c_int, [_vp, ct.c_int, ct.POINTER(Track)]),
+    "gofpid_tracker_contour": (ct.c_int, [_vp, ct.c_int, _vp, ct.c_int]),
+    "gofpid_tracker_alarm_state": (ct.c_int, [_vp, ct.POINTER(ct.c_int), ct.POINTER(ct.c_double)]),
     "gofpid_blur_u8": (ct.c_int, [_vp, _sz, _vp, _sz, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_int,
                                   ct.c_int, ct.c_double, _vp]),
     "gofpid_morph_u8": (ct.c_int, [_vp, _sz, _vp, _sz, ct.c_int, ct.c_int, ct.POINTER(MorphOp), ct.c_int,

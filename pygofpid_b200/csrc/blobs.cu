@@ -41,12 +41,13 @@ constexpr int CCL_THREADS = 16 * CCL_TH; // each thread owns 4 consecutive pixel
 #ifndef GOFPID_TRACE_LOG2_CP
 #define GOFPID_TRACE_LOG2_CP 12
 #endif
-constexpr int TRACE_THREADS = GOFPID_TRACE_THREADS;
-constexpr int TRACE_MAX_CP = 1 << GOFPID_TRACE_LOG2_CP;     // checkpoints per contour
-constexpr int TRACE_HT = 2 * TRACE_MAX_CP;                  // hash slots (power of two, >= 2 * TRACE_MAX_CP)
-constexpr int TRACE_HT_SHIFT = 32 - (GOFPID_TRACE_LOG2_CP + 1); // 32 - log2(TRACE_HT)
-// per checkpoint: a00 (8 B) + state, length, two (next, distance) pairs (24 B)
-constexpr size_t TRACE_SMEM_BYTES = (size_t)TRACE_MAX_CP * (8 + 24) + (size_t)TRACE_HT * 8;
+// (Measured and dropped in round 2: blob kernels sized to fit beside resident detector CTAs -- a 128-thread
+// labeller with a 16-bit forest in 26 KB, a 128-thread / 512-checkpoint instance of this tracer, and a
+// one-warp-per-component sequential tracer.  All bit-exact, all slower for the whole step than the SM-sized
+// kernels below: 25.5 / 25.5 / 91 us per 1080p frame against 22.9, see DESIGN.md.)
+constexpr int TRACE_THREADS = GOFPID_TRACE_THREADS, TRACE_LOG2_CP = GOFPID_TRACE_LOG2_CP;
+// per checkpoint: a00 (8 B) + state, length, two (next, distance) pairs (24 B); hash: 2 slots of 8 B per checkpoint
+constexpr size_t trace_smem_bytes(int log2_cp) { return ((size_t)1 << log2_cp) * (8 + 24) + ((size_t)2 << log2_cp) * 8; }
 
 // component record layout (8 int32)
 enum { CR_FIRST = 0, CR_X0, CR_Y0, CR_X1, CR_Y1, CR_AREA, CR_RSTART, CR_NRUNS, CR_SIZE }; // (run slice: runs path only)
@@ -848,22 +849,26 @@ __device__ __forceinline__ bool cp_hash(int x, int y, unsigned rmask)
 }
 __device__ __forceinline__ int cp_key(int x, int y, int b) { return ((y << 16) | (x << 3) | b) + 1; }
 
+template <int LOG2_HT>
 __device__ __forceinline__ int ht_find(const int *keys, const int *vals, int key)
 {
-    unsigned h = ((unsigned)key * 0x9E3779B1u) >> TRACE_HT_SHIFT;
+    constexpr int HT = 1 << LOG2_HT;
+    unsigned h = ((unsigned)key * 0x9E3779B1u) >> (32 - LOG2_HT);
     while (true) {
-        const int k = keys[h & (TRACE_HT - 1)];
-        if (k == key) return vals[h & (TRACE_HT - 1)];
+        const int k = keys[h & (HT - 1)];
+        if (k == key) return vals[h & (HT - 1)];
         if (k == 0) return -1;
         h++;
     }
 }
+template <int LOG2_HT>
 __device__ __forceinline__ void ht_insert(int *keys, int *vals, int key, int val)
 {
-    unsigned h = ((unsigned)key * 0x9E3779B1u) >> TRACE_HT_SHIFT;
+    constexpr int HT = 1 << LOG2_HT;
+    unsigned h = ((unsigned)key * 0x9E3779B1u) >> (32 - LOG2_HT);
     while (true) {
-        const int old = atomicCAS(&keys[h & (TRACE_HT - 1)], 0, key);
-        if (old == 0 || old == key) { vals[h & (TRACE_HT - 1)] = val; return; }
+        const int old = atomicCAS(&keys[h & (HT - 1)], 0, key);
+        if (old == 0 || old == key) { vals[h & (HT - 1)] = val; return; }
         h++;
     }
 }
@@ -874,7 +879,7 @@ struct SegSums { long long a00, a10, a01; };
 // visited points, otherwise the Green sums of cv.contourArea / cv.moments are accumulated
 // (a step from p to q contributes dxy = p.x*q.y - q.x*p.y, dxy*(p.x+q.x), dxy*(p.y+q.y)).
 // Returns the id of the checkpoint reached (-1: none within max_steps).
-template <bool STORE>
+template <bool STORE, int LOG2_HT>
 __device__ int trace_segment(const BitView &V, int x, int y, int b, int xs, int ys, unsigned rmask,
                              const int *keys, const int *vals, int &len, SegSums &S, int32_t *pts,
                              int max_steps)
@@ -896,7 +901,7 @@ __device__ int trace_segment(const BitView &V, int x, int y, int b, int xs, int 
         n++;
         x += dx; y += dy; b = (s + 4) & 7;
         if (cp_hash(x, y, rmask) || (x == xs && y == ys)) {
-            id = ht_find(keys, vals, cp_key(x, y, b));
+            id = ht_find<LOG2_HT>(keys, vals, cp_key(x, y, b));
             if (id >= 0) break;
         }
     }
@@ -905,12 +910,16 @@ __device__ int trace_segment(const BitView &V, int x, int y, int b, int xs, int 
     return id;
 }
 
+template <int TRACE_THREADS, int LOG2_CP>
 __global__ void __launch_bounds__(TRACE_THREADS)
 trace_kernel(const int32_t *labels, size_t LP, size_t labels_stream, RunList R, const int32_t *comp,
              gofpid_frame_info *info, gofpid_blob *kept, int32_t *points, int max_blobs,
              int max_kept, int max_points, double area_min, const uint32_t *bitimg, int bit_pitch,
              size_t bit_stream, int H, int W)
 {
+    constexpr int TRACE_MAX_CP = 1 << LOG2_CP;  // checkpoints per contour
+    constexpr int TRACE_HT = 2 * TRACE_MAX_CP;  // hash slots
+    constexpr int LOG2_HT = LOG2_CP + 1;
     extern __shared__ __align__(16) unsigned char tsm[];
     long long *seg_a00 = reinterpret_cast<long long *>(tsm);             // per checkpoint
     int *ht_keys = reinterpret_cast<int *>(seg_a00 + TRACE_MAX_CP);
@@ -922,7 +931,7 @@ trace_kernel(const int32_t *labels, size_t LP, size_t labels_stream, RunList R, 
     unsigned *dA = reinterpret_cast<unsigned *>(nxtB + TRACE_MAX_CP);
     unsigned *dB = dA + TRACE_MAX_CP;
     __shared__ int sh_ncp, sh_ncand, sh_keep, sh_off;
-    __shared__ long long sh_part[3][32];
+    __shared__ long long sh_part[3][TRACE_THREADS / 32];
     const int z = blockIdx.y;
     const int32_t *lab = labels + (size_t)z * labels_stream;
     gofpid_frame_info *fi = info + z;
@@ -1063,7 +1072,7 @@ trace_kernel(const int32_t *labels, size_t LP, size_t labels_stream, RunList R, 
             if (!retry) {
                 if (tid == 0) {
                     cp_state[0] = (ys << 16) | (xs << 3) | b0;
-                    ht_insert(ht_keys, ht_vals, cp_key(xs, ys, b0), 0);
+                    ht_insert<LOG2_HT>(ht_keys, ht_vals, cp_key(xs, ys, b0), 0);
                 }
                 for (int k = tid; k < ncand; k += TRACE_THREADS) {
                     const int x = cand_list[k] & 0xffff, y = cand_list[k] >> 16;
@@ -1074,7 +1083,7 @@ trace_kernel(const int32_t *labels, size_t LP, size_t labels_stream, RunList R, 
                         if (slot >= TRACE_MAX_CP) break;
                         const int bdir = __ffs(st) - 1;
                         cp_state[slot] = (y << 16) | (x << 3) | bdir;
-                        ht_insert(ht_keys, ht_vals, cp_key(x, y, bdir), slot);
+                        ht_insert<LOG2_HT>(ht_keys, ht_vals, cp_key(x, y, bdir), slot);
                     }
                 }
                 __syncthreads();
@@ -1093,7 +1102,7 @@ trace_kernel(const int32_t *labels, size_t LP, size_t labels_stream, RunList R, 
             const int st = cp_state[i];
             int len;
             SegSums S;
-            const int nx = trace_segment<false>(bv, (st >> 3) & 8191, st >> 16, st & 7, xs, ys, rmask,
+            const int nx = trace_segment<false, LOG2_HT>(bv, (st >> 3) & 8191, st >> 16, st & 7, xs, ys, rmask,
                                                 ht_keys, ht_vals, len, S, nullptr, max_steps);
             seg_a00[i] = S.a00;
             seg_len[i] = len;
@@ -1172,7 +1181,7 @@ trace_kernel(const int32_t *labels, size_t LP, size_t labels_stream, RunList R, 
                     const int st = cp_state[i];
                     int len;
                     SegSums S;
-                    trace_segment<true>(bv, (st >> 3) & 8191, st >> 16, st & 7, xs, ys, rmask, ht_keys,
+                    trace_segment<true, LOG2_HT>(bv, (st >> 3) & 8191, st >> 16, st & 7, xs, ys, rmask, ht_keys,
                                         ht_vals, len, S, dst + 2 * (size_t)nbuf[i], max_steps);
                     a10 += S.a10; a01 += S.a01;
                 }
@@ -1238,7 +1247,7 @@ __global__ void __launch_bounds__(256)
 nest_kernel(gofpid_frame_info *info, gofpid_blob *kept, const int32_t *points, int max_kept, int max_points,
             int W)
 {
-    constexpr int CAP = 2048; // boxes staged in shared memory (further blobs are read from global)
+    constexpr int CAP = 1024; // boxes staged in shared memory (further blobs are read from global)
     __shared__ short4 box[CAP];
     const int z = blockIdx.y;
     gofpid_frame_info *fi = info + z;
@@ -1448,10 +1457,11 @@ int launch_blobs(const BlobBuffers &B, ImageU8 mask, int H, int W, int n_streams
         GOFPID_TRY(launch_fallback(B, mask, H, W, n_streams, s));
         n += 4;
     }
-    GOFPID_CUDA_TRY(cudaFuncSetAttribute(trace_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                         (int)TRACE_SMEM_BYTES));
+    constexpr size_t sm = trace_smem_bytes(TRACE_LOG2_CP);
+    GOFPID_CUDA_TRY(cudaFuncSetAttribute(trace_kernel<TRACE_THREADS, TRACE_LOG2_CP>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm));
     const dim3 cgrid(n_streams >= 64 ? 8 : (n_streams >= 8 ? 32 : 148), n_streams);
-    trace_kernel<<<cgrid, TRACE_THREADS, TRACE_SMEM_BYTES, s>>>(
+    trace_kernel<TRACE_THREADS, TRACE_LOG2_CP><<<cgrid, TRACE_THREADS, sm, s>>>(
         B.labels, B.labels_pitch, B.labels_stream, B.runs, B.comp, B.info, B.kept, B.points, B.max_blobs,
         B.max_kept, B.max_points, B.area_min, B.bitimg, B.bit_pitch, B.bit_stream, H, W);
     GOFPID_CUDA_TRY(cudaGetLastError());

@@ -44,6 +44,7 @@ struct Tuning {
     int morph_bytes = 0;  // GOFPID_MORPH_BYTES=1: byte morphology kernel inside the pipeline
     int knn_scalar = 0;   // GOFPID_KNN_SCALAR=1: general KNN kernel on gray frames too (tests)
     int runs_cap = -1;    // GOFPID_RUNS_CAP: run capacity of the shared-memory labeller (tests: force the fallback)
+    int mog2_smem_pad = 0; // GOFPID_MOG2_SMEM_PAD: extra dynamic shared memory per MOG2 CTA (caps the CTAs per SM: A/B measurements)
     int mog2_generic = 0; // GOFPID_MOG2_GENERIC=1: the generic MOG2 kernel even for ordinary parameters (tests)
     int event_timing = 0; // GOFPID_EVENT_TIMING=1: slot events keep timestamps (debug build tools)
 };
@@ -124,6 +125,7 @@ struct Mog2Params {
     int detectShadows, shadowVal, history;
     float ct;
     int force_generic; // Tuning::mog2_generic: never take the lean kernel
+    int smem_pad;      // Tuning::mog2_smem_pad
 };
 // MOG2 model, tiled: per stream tiles_x * tiles_y tiles of MOG2_TILE_W x MOG2_TILE_H pixels; a
 // tile is one contiguous block [mode][plane: weight, var, mean c..][512 px] of floats, so its

@@ -46,6 +46,7 @@ Tuning read_tuning()
     t.runs_cap = num("GOFPID_RUNS_CAP", 0, 1 << 30, -1);
     t.event_timing = flag("GOFPID_EVENT_TIMING", '1');
     t.mog2_generic = flag("GOFPID_MOG2_GENERIC", '1');
+    t.mog2_smem_pad = num("GOFPID_MOG2_SMEM_PAD", 0, 65536, 0);
     return t;
 }
 
@@ -331,6 +332,7 @@ int build(gofpid_pipeline *p)
     mp.tau = cfg.shadow_tau; mp.detectShadows = cfg.detect_shadows; mp.shadowVal = cfg.shadow_value;
     mp.history = cfg.mog2_history; mp.ct = cfg.mog2_ct;
     mp.force_generic = p->tune.mog2_generic;
+    mp.smem_pad = p->tune.mog2_smem_pad;
     KnnParams &kp = p->knnp;
     kp.Tb = cfg.knn_dist2_threshold; kp.tau = cfg.shadow_tau; kp.knn = cfg.knn_k;
     kp.detectShadows = cfg.detect_shadows; kp.shadowVal = cfg.shadow_value; kp.history = cfg.knn_history;
@@ -934,13 +936,14 @@ int stage_host_frames(gofpid_pipeline *p, int ahead, const uint8_t *h_frames, si
     return GOFPID_OK;
 }
 
-// g consecutive frames of a dense pinned clip -> g consecutive slots with ONE copy (a 2 MB frame
-// alone does not reach the link's bandwidth); anything else goes frame by frame.
-int stage_host_group(gofpid_pipeline *p, int g, const uint8_t *h_frames, size_t frame_stride, size_t pitch,
+// g consecutive frames of a dense pinned clip -> g consecutive slots (starting `ahead` slots after the
+// next one) with ONE copy: copies of a frame or three do not reach the link's bandwidth, half a ring of
+// slots does (tools/pcie_bw.py); anything else goes frame by frame.
+int stage_host_group(gofpid_pipeline *p, int ahead, int g, const uint8_t *h_frames, size_t frame_stride, size_t pitch,
                      size_t stream_stride)
 {
     const size_t row = (size_t)p->W * p->Csrc;
-    const int s0 = (int)(p->frames % p->depth);
+    const int s0 = (int)((p->frames + ahead) % p->depth);
     bool one = g > 1 && s0 + g <= p->depth && p->d_frames_base && pitch >= row &&
                (p->n_streams == 1 || stream_stride == pitch * (size_t)p->H) &&
                frame_stride == pitch * (size_t)p->H * p->n_streams;
@@ -953,7 +956,7 @@ int stage_host_group(gofpid_pipeline *p, int g, const uint8_t *h_frames, size_t 
     }
     if (!one) {
         for (int f = 0; f < g; f++)
-            GOFPID_TRY(stage_host_frames(p, f, h_frames + (size_t)f * frame_stride, pitch, stream_stride));
+            GOFPID_TRY(stage_host_frames(p, ahead + f, h_frames + (size_t)f * frame_stride, pitch, stream_stride));
         return GOFPID_OK;
     }
     cudaStream_t sh = p->stream_h;
@@ -1033,13 +1036,24 @@ int run_sequence(gofpid_pipeline *p, const uint8_t *frames, bool host, int n_fra
         }
         return GOFPID_OK;
     };
+    int staged = 0; // frames of this clip whose host->device copy has been issued
+    // Host clips are uploaded half a ring of frame slots at a time, ahead of the frames being enqueued:
+    // the copy of the next chunk only waits for the detector launches that read the slots' previous
+    // frames, so the copy engine stays busy with large transfers while the detector works on the
+    // chunk before.
+    const int chunk = std::max(1, p->depth / 2);
     while (t < n_frames) {
         int g = 1;
         if (p->group > 1 && p->frames >= p->depth && p->use_graph) g = std::min(p->group, n_frames - t);
         // frames t .. t+g-1 take the slots of frames t-depth .. t+g-1-depth: collect those first
         if (h_counts) GOFPID_TRY(collect(t + g - 1 - p->depth));
         const uint8_t *ptr[MOG2_MAX_GROUP];
-        if (host) GOFPID_TRY(stage_host_group(p, g, frames + (size_t)t * frame_stride, frame_stride, pitch, stream_stride));
+        while (host && staged < t + g) {
+            const int s0 = (int)((p->frames + (staged - t)) % p->depth);
+            const int n = std::min(std::min(chunk, n_frames - staged), p->depth - s0); // (a copy does not wrap around the ring)
+            GOFPID_TRY(stage_host_group(p, staged - t, n, frames + (size_t)staged * frame_stride, frame_stride, pitch, stream_stride));
+            staged += n;
+        }
         for (int f = 0; f < g; f++)
             ptr[f] = host ? p->slots[(p->frames + f) % p->depth].d_frames : frames + (size_t)(t + f) * frame_stride;
         p->from_host = host;

@@ -259,7 +259,13 @@ class HotPath:
                 continue
             nat.check(rc)
             out = pts[:npt.value]
-            return recs[:nb.value], (out.copy() if copy else out)
+            if not copy:
+                return recs[:nb.value], out
+            # an own copy of the records too (a ctypes array of gofpid_blob) and of the points
+            own = (nat.Blob * max(nb.value, 1))()
+            ct.memmove(own, recs, nb.value * ct.sizeof(nat.Blob))
+            own_t = (nat.Blob * nb.value).from_buffer(own) if nb.value else (nat.Blob * 0)()
+            return own_t, out.copy()
 
     def process_sequence(self, frames, blob_capacity=None, point_capacity=None):
         """A whole clip from HOST memory -- or a CUDA uint8 tensor -- in one library call

@@ -98,6 +98,10 @@ class GOFPID():
     depth : int, default=0
         Frame slots of the GPU pipeline (0 = default: deep, for `detect_clip`); `detect` alone never
         has more than one frame in flight and works with depth=2 (saves device memory).
+    tail : {'native', 'python'}, default='native'
+        Who runs steps 5-7 (tracking, post-filter, alarm): the C++ tracker of libgofpid_b200
+        (`gofpid_tracker`, same results, a few microseconds per frame; `blobs_` and `tracked_blobs_` are
+        then built from its state when they are read) or the Python methods of this class.
 
     Attributes
     ----------
@@ -123,6 +127,7 @@ class GOFPID():
         max_kept=4096,
         max_points=0,
         depth=0,
+        tail='native',
     ):
         self.convert = convert
         self.blur = blur
@@ -138,6 +143,7 @@ class GOFPID():
         self.max_kept = max_kept
         self.max_points = max_points
         self.depth = depth
+        self.tail = tail
 
     # ------------------------------------------------------------------ configuration
     def initialize(self):
@@ -178,15 +184,52 @@ class GOFPID():
             if key not in self.alarm_def.keys():
                 raise KeyError('Parameter alarm_def has no key "%s".' % key)
 
+        if self.tail not in ('native', 'python'):
+            raise ValueError('Parameter tail must be "native" or "python".')
         self._plan = self._hot_path_plan()
         self._engine = None           # created on the first frame (the shape is needed)
         self._host_estimator = ViBe() if self.frg_detect == 'ViBe' else None
         self._mask_cache = None
+        self._tail = None             # native tracker, created with the first frame `detect` sees
+        self._raw = None              # (records, points) of the last frame when the native tail is in use
         self.blobs_ = []
         self.tracked_blobs_ = []
         self.input_shape_ = None
         self._alarm_system = {'already_in_alarm': False, 'duration': 0}
         return self
+
+    # `blobs_` / `tracked_blobs_` are plain lists with the Python tail.  With the native tail they are
+    # built when read: from the last frame's blob records, and from the tracker's state.
+    @property
+    def blobs_(self):
+        if self._raw is not None:
+            from .hotpath import blobs_from_records
+            self._blobs_py = blobs_from_records(self._raw[0], self._raw[1], self.post_filter['anchor'])
+            self._raw = None
+        return self._blobs_py
+
+    @blobs_.setter
+    def blobs_(self, value):
+        self._raw = None
+        self._blobs_py = value
+
+    @property
+    def tracked_blobs_(self):
+        if getattr(self, '_tail', None) is not None:
+            return self._tail.tracks()
+        return self._tracked_py
+
+    @tracked_blobs_.setter
+    def tracked_blobs_(self, value):
+        self._tracked_py = value
+
+    def _native_tail(self):
+        """The C++ tracker of this stream (created after the first-frame calibration)."""
+        if self._tail is None:
+            from .tail import NativeTail
+            self._tail = NativeTail(self.input_shape_[0], self._perspective['height'], self._perspective['area'],
+                                    self.post_filter['perimeter'], self.tracking, self.post_filter, self.alarm_def)
+        return self._tail
 
     def _hot_path_plan(self):
         """Translate the reference's OpenCV-flavoured parameters into kernel configuration."""
@@ -296,7 +339,17 @@ class GOFPID():
             self._hot_path(X, fused)
         else:
             self._hot_path_host_estimator(X)
+        return self._run_tail()
 
+    def _run_tail(self):
+        """Steps 5-7 on the blobs of the frame that just went through the GPU."""
+        if self.tail == 'native':
+            recs, pts = self._raw
+            y = self._native_tail().step_records(recs, len(recs), pts)
+            if self.verbose and y and not self._alarm_system['already_in_alarm']:
+                print("Intrusion detected")
+            self._alarm_system = self._tail.alarm_state() if self.verbose else self._alarm_system
+            return y
         self._track_blob()       # step 5
         self._post_filter()      # step 6
         y = self._detect_blob()  # step 7
@@ -330,6 +383,13 @@ class GOFPID():
         frames = X[..., 0] if (X.ndim == 4 and X.shape[3] == 1) else X
         counts, recs, pts = self._engine.process_sequence(frames)
         self._mask_cache = None
+        if self.tail == 'native':
+            out = self._native_tail().run(counts, recs, pts)
+            nb, npt = int(counts[-1, 0, 0]), int(counts[-1, 0, 1])
+            self._raw = (recs[len(recs) - nb:], pts[len(pts) - npt:])  # blobs_ of the last frame, built when read
+            if self.verbose and any(out):
+                print("Intrusion detected")
+            return out
         out, ob, op = [], 0, 0
         for t in range(X.shape[0]):
             nb, npt = int(counts[t, 0, 0]), int(counts[t, 0, 1])
@@ -365,7 +425,15 @@ class GOFPID():
                                             self._plan['morph'], convert)
         self._engine.process(X)
         self._mask_cache = None
-        self.blobs_ = self._engine.blobs(anchor=self.post_filter['anchor'])
+        self._take_blobs()
+
+    def _take_blobs(self):
+        """blobs_ of the frame the engine just finished: dictionaries for the Python tail, the raw records
+        for the native one (dictionaries are then only built if somebody reads blobs_)."""
+        if self.tail == 'native':
+            self._raw = self._engine.raw_blobs()
+        else:
+            self.blobs_ = self._engine.blobs(anchor=self.post_filter['anchor'])
 
     def _hot_path_host_estimator(self, X):
         """ViBe keeps its host-side model (see segmentation.ViBe); blur before it and
@@ -386,7 +454,7 @@ class GOFPID():
         self._engine.process(np.zeros_like(mask))
         self._engine.process(mask)
         self._mask_cache = None
-        self.blobs_ = self._engine.blobs(anchor=self.post_filter['anchor'])
+        self._take_blobs()
 
     # ------------------------------------------------------------------ calibration
     def _calib_first_frame(self):

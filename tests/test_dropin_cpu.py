@@ -220,6 +220,108 @@ def test_host_tail_matches_the_reference_on_busy_blob_streams(trial):
         assert sum(len(tr['filtered']) for tr in g.tracked_blobs_) == int(want["nfiltered_%d" % trial][t]), t
 
 
+@pytest.mark.parametrize("trial", range(12))
+def test_native_tail_matches_the_reference_on_busy_blob_streams(trial):
+    """The C++ tracker of libgofpid_b200 (gofpid_tracker: pure host code, no GPU needed) on the same streams:
+    alarm, number of tracks, summed presence and number of active filters of every frame are what the REAL
+    reference answered, and its tracks equal those of the Python tail field by field."""
+    import os
+    import warnings
+    from golden_cases import GOLDEN_DIR, tail_post_filter, tail_stream
+    want = np.load(os.path.join(GOLDEN_DIR, "tail_streams.npz"))
+    H, W, kind, frames = tail_stream(trial)
+    g = GOFPID(post_filter=tail_post_filter(kind)).initialize()
+    g.input_shape_ = (H, W)
+    g._calib_first_frame()
+    tail = g._native_tail()
+    py = GOFPID(post_filter=tail_post_filter(kind), tail='python').initialize()
+    py.input_shape_ = (H, W)
+    py._calib_first_frame()
+    for t, blobs in enumerate(frames):
+        y = tail.step_dicts(blobs)
+        tracks = g.tracked_blobs_
+        assert bool(y) == bool(want["alarm_%d" % trial][t]), t
+        assert len(tracks) == len(tail) == int(want["ntracked_%d" % trial][t]), t
+        assert sum(tr['presence'] for tr in tracks) == int(want["presence_%d" % trial][t]), t
+        assert sum(len(tr['filtered']) for tr in tracks) == int(want["nfiltered_%d" % trial][t]), t
+        py.blobs_ = blobs
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            py._track_blob()
+            py._post_filter()
+            yp = py._maintain_alarm(py._detect_blob())
+        assert yp == y
+        if t % 10 == 0 or t == len(frames) - 1:
+            for a, b in zip(tracks, py.tracked_blobs_):
+                for key in ('anchor', 'bottom', 'center', 'center_first', 'contour'):
+                    assert np.array_equal(a[key], b[key]) and a[key].dtype == np.asarray(b[key]).dtype, (t, key)
+                for key in ('presence', 'absence', 'filtered', 'already_in_alarm'):
+                    assert a[key] == b[key], (t, key)
+    state = tail.alarm_state()
+    assert state['already_in_alarm'] == py._alarm_system['already_in_alarm'] and state['duration'] == py._alarm_system['duration']
+
+
+@pytest.mark.parametrize("name", ["fd_gray_open3", "mog2_gray_default", "mog2_bgr_default", "knn_gray_default"])
+def test_native_tail_replays_the_reference_tracks_and_alarms(name):
+    """... and on the blob lists the REAL reference produced on the pipeline goldens."""
+    from golden_cases import golden_blobs, load
+    g = load(name)
+    H, W, C = (int(v) for v in g["shape"])
+    pf = {'perimeter': None, 'anchor': 'bottom', 'perspective': None, 'perspective_coeff': 0.5,
+          'presence_min': 3, 'distance_min': 0.25}  # (the constructor's default dict is shared and mutated, as in the reference)
+    gofpid = GOFPID(post_filter=pf).initialize()
+    gofpid.input_shape_ = (H, W) if C == 1 else (H, W, C)
+    gofpid._calib_first_frame()
+    tail = gofpid._native_tail()
+    for t in range(int(g["n"])):
+        blobs = golden_blobs(g, t)
+        for b in blobs:
+            b["center"] = np.asarray(b["center"], np.int16)
+            b["bottom"] = np.asarray(b["bottom"], np.int16)
+            b["anchor"] = b["bottom"]
+        assert tail.step_dicts(blobs) == bool(g["alarm"][t]), (name, t)
+        assert len(tail) == int(g["ntracked"][t]), (name, t)
+
+
+def test_native_tail_degenerate_geometry_follows_the_reference_types():
+    """int16 wrap-around of squared centre differences, zero radii, empty frames: the C++ tracker and the
+    Python tail (which evaluates the reference's expressions in NumPy's own types) agree."""
+    import warnings
+    rs = np.random.RandomState(4)
+    H, W = 1080, 1920
+    for trial in range(4):
+        pf = {'perimeter': None, 'anchor': 'center' if trial % 2 else 'bottom', 'perspective': None,
+              'perspective_coeff': 0.5, 'presence_min': 2, 'distance_min': 0.0 if trial == 3 else 0.2}
+        trk = {'factor': (1.5, 40.0, 0.01, 3.0)[trial], 'absence_max': 3}
+        a = GOFPID(post_filter=dict(pf), tracking=dict(trk)).initialize()
+        b = GOFPID(post_filter=dict(pf), tracking=dict(trk), tail='python').initialize()
+        for g in (a, b):
+            g.input_shape_ = (H, W)
+            g._calib_first_frame()
+        tail = a._native_tail()
+        for t in range(60):
+            blobs = []
+            for _ in range(rs.randint(0, 6)):
+                x0, y0, w, h = rs.randint(0, W - 300), rs.randint(0, H - 300), rs.randint(2, 300), rs.randint(2, 300)
+                c = np.array([[x0, y0], [x0 + w, y0], [x0 + w, y0 + h], [x0, y0 + h]], np.int32).reshape(-1, 1, 2)
+                bottom = np.array([x0 + w // 2, y0 + h], np.int16)
+                center = np.array([x0 + w // 2, y0 + h // 2], np.int16)
+                blobs.append(dict(contour=c, anchor=center if trial % 2 else bottom, bottom=bottom, center=center))
+            ya = tail.step_dicts(blobs)
+            b.blobs_ = blobs
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                b._track_blob()
+                b._post_filter()
+                yb = b._maintain_alarm(b._detect_blob())
+            assert ya == yb, (trial, t)
+            ta, tb = a.tracked_blobs_, b.tracked_blobs_
+            assert len(ta) == len(tb), (trial, t)
+            for u, v in zip(ta, tb):
+                assert u['filtered'] == v['filtered'] and u['presence'] == v['presence'] and u['absence'] == v['absence']
+                assert np.array_equal(u['center'], v['center']) and np.array_equal(u['center_first'], v['center_first'])
+
+
 @pytest.mark.skipif(cv is None, reason="display() draws with OpenCV")
 @pytest.mark.parametrize("trial", [0, 3])
 def test_display_draws_what_the_reference_draws(trial):

@@ -274,6 +274,65 @@ def test_blobs_match_reference_semantics(runs_cap, monkeypatch):
             hp.close()
 
 
+@pytest.mark.parametrize("runs_cap", [None, 64])
+def test_device_clip_blob_stage_matches_reference_semantics(runs_cap, monkeypatch):
+    """The blob stage as device-resident clips run it (stage-B graphs replayed per frame slot, the tiled
+    fallback behind a conditional graph node): the masks of test_blobs_match_reference_semantics -- noise,
+    rings, nesting, full and empty frames -- plus large blobs with long ragged borders (more visits than the
+    tracer has checkpoints, so borders are walked in thinned segments), one clip per shape through
+    process_sequence on a CUDA tensor; every frame's blob list, the last frame's labels and statistics
+    against the oracle.  runs_cap=64: busy frames raise the conditional node in between calm ones."""
+    import cv2
+    import torch
+    from pygofpid_b200.hotpath import blobs_from_records
+    if runs_cap is not None:
+        monkeypatch.setenv("GOFPID_RUNS_CAP", str(runs_cap))
+    rs = np.random.RandomState(21)
+    clips = {}
+    for M in _blob_masks():
+        clips.setdefault(M.shape, []).append(M)
+    big = []
+    for it in range(6):  # blobs with borders far longer than 512 visits, holes, thin bridges
+        M = np.zeros((300, 420), np.uint8)
+        for _ in range(5):
+            c = (int(rs.randint(40, 380)), int(rs.randint(40, 260)))
+            cv2.ellipse(M, c, (int(rs.randint(20, 120)), int(rs.randint(15, 90))), float(rs.randint(0, 180)), 0, 360, 255, -1)
+        M[rs.rand(*M.shape) < 0.08] = 0
+        if it % 2:
+            M = cv2.dilate(M, np.ones((3, 3), np.uint8))
+        big.append(M)
+    clips[(300, 420)] = big
+    n_checked = 0
+    for (H, W), masks in clips.items():
+        for area_min in (100.0, 0.5):
+            hp = _hot((H, W), blur=None, detector="FD", morph=(), find_blobs=True, fd_threshold=0, area_min=area_min, depth=2)
+            # FD yields |frame - previous| > 0: frames whose differences are the wanted masks; two empty
+            # frames first (the first `depth` steps of a handle run eagerly, graphs replay from then on)
+            seq_masks = [np.zeros((H, W), np.uint8)] * 3 + list(masks)
+            frames, prev = [], np.zeros((H, W), np.uint8)
+            for M in seq_masks:
+                prev = np.where(M > 0, 255 - prev, prev).astype(np.uint8)
+                frames.append(prev)
+            counts, recs, pts = hp.process_sequence(torch.from_numpy(np.stack(frames)).cuda())
+            ob = op = 0
+            for t, M in enumerate(seq_masks):
+                nb, npt = int(counts[t, 0, 0]), int(counts[t, 0, 1])
+                got = blobs_from_records(recs[ob:ob + nb], pts[op:op + npt])
+                ob += nb; op += npt
+                want = oblobs.blobs_from_mask(np.where(M > 0, 255, 0).astype(np.uint8), area_min=area_min)
+                assert len(got) == len(want), ((H, W), t, area_min, len(got), len(want))
+                for g, w in zip(got, want):
+                    assert np.array_equal(g["contour"], w["contour"]), ((H, W), t, area_min)
+                    assert np.array_equal(g["center"], w["center"]) and np.array_equal(g["bottom"], w["bottom"])
+                n_checked += 1
+            want_mask = np.where(seq_masks[-1] > 0, 255, 0).astype(np.uint8)
+            assert np.array_equal(hp.mask(), want_mask)
+            assert np.array_equal(hp.labels(), cport.ccl8(want_mask))
+            assert hp.components() == cport.component_stats(cport.ccl8(want_mask))
+            hp.close()
+    assert n_checked > 50
+
+
 @pytest.mark.parametrize("no_cond", ["0", "1"])
 def test_graph_replay_switches_between_run_and_tiled_labelling(no_cond, monkeypatch):
     """Frames alternate between a few blobs (run-based labelling) and dense noise (more runs than the

@@ -16,6 +16,7 @@ import torch
 ap = argparse.ArgumentParser()
 ap.add_argument("--affinity", action="store_true")
 ap.add_argument("--wc", action="store_true")
+ap.add_argument("--sizes", default="2,6,64", help="copy sizes in MB")
 args = ap.parse_args()
 rank, world, local = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("WORLD_SIZE", 1), ("LOCAL_RANK", 0)))
 torch.cuda.set_device(local)
@@ -39,7 +40,7 @@ try:
 except Exception as e:  # topology files are best effort
     print("rank %d: topology lookup failed: %s" % (rank, e))
 from pygofpid_b200.hotpath import PinnedFrames
-for mb in (2, 6, 64):
+for mb in ([int(v) for v in args.sizes.split(',')]):
     n = mb * 1024 * 1024
     if args.wc:
         keep = PinnedFrames((n,), write_combined=True)
