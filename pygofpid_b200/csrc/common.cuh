@@ -44,6 +44,7 @@ struct Tuning {
     int morph_bytes = 0;  // GOFPID_MORPH_BYTES=1: byte morphology kernel inside the pipeline
     int knn_scalar = 0;   // GOFPID_KNN_SCALAR=1: general KNN kernel on gray frames too (tests)
     int runs_cap = -1;    // GOFPID_RUNS_CAP: run capacity of the shared-memory labeller (tests: force the fallback)
+    int h2d_chunk = 0;    // GOFPID_H2D_CHUNK: frames per host->device copy of a host clip (0: the frames of one detector launch)
     int mog2_smem_pad = 0; // GOFPID_MOG2_SMEM_PAD: extra dynamic shared memory per MOG2 CTA (caps the CTAs per SM: A/B measurements)
     int mog2_generic = 0; // GOFPID_MOG2_GENERIC=1: the generic MOG2 kernel even for ordinary parameters (tests)
     int event_timing = 0; // GOFPID_EVENT_TIMING=1: slot events keep timestamps (debug build tools)
@@ -156,7 +157,7 @@ struct KnnParams {
     int knn, detectShadows, shadowVal, history;
 };
 struct KnnModel {
-    uint8_t *samples;      // per stream: 21 planes of PW*H*(C+1) bytes
+    uint8_t *samples;      // per stream: 21 planes of PW*H*(C+1) bytes; gray: four pixels = (v0 v1 v2 v3 | f0 f1 f2 f3), colour: (c0 c1 c2 flag) per pixel
     uint32_t *nxt;         // per stream: PW*H words (nxtS | nxtM<<8 | nxtL<<16)
     uint16_t *idx;         // per stream: PW*H halfwords (idxS | idxM<<3 | idxL<<6)
     uint8_t *fresh;        // per stream: 3 dense arrays of H*W bytes (RNG fills S, M, L)

@@ -12,7 +12,11 @@
 #include <string.h>
 
 #include <algorithm>
+#include <atomic>
+#include <condition_variable>
+#include <mutex>
 #include <new>
+#include <thread>
 #include <vector>
 
 namespace gofpid {
@@ -47,6 +51,7 @@ Tuning read_tuning()
     t.event_timing = flag("GOFPID_EVENT_TIMING", '1');
     t.mog2_generic = flag("GOFPID_MOG2_GENERIC", '1');
     t.mog2_smem_pad = num("GOFPID_MOG2_SMEM_PAD", 0, 65536, 0);
+    t.h2d_chunk = num("GOFPID_H2D_CHUNK", 0, 16, 0);
     return t;
 }
 
@@ -70,7 +75,96 @@ constexpr int DEFAULT_DEPTH_MOG2 = 12, DEFAULT_DEPTH_MOG2_MANY = 8;
 // (GOFPID_MOG2_GROUP overrides: 1 .. MOG2_MAX_GROUP, at most half the slots)
 // (GOFPID_DEPTH overrides: 1 .. MAX_DEPTH)
 
+// Pageable host frames (what cv.VideoCapture.read() hands to GOFPID.detect) have to pass through page-locked
+// memory before the copy engine can take them.  One thread moves 2 MB in about 200 us -- five times what the
+// frame then needs over the link -- so the rows of a frame are split over a few persistent worker threads
+// (fork / join per frame), and every frame slot has its own page-locked buffer so that filling the next one
+// overlaps the upload of the previous one.
+class HostCopier {
+public:
+    explicit HostCopier(int workers)
+    {
+        for (int i = 0; i < workers; i++) th_.emplace_back([this] { worker(); });
+    }
+    ~HostCopier()
+    {
+        {
+            std::lock_guard<std::mutex> lk(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (auto &t : th_) t.join();
+    }
+    // nrows rows of `row` bytes, source rows spitch apart, destination rows dpitch apart.  The rows are cut
+    // into chunks that the caller and whichever workers are awake take one after the other: a worker that
+    // wakes up late (a synchronous per-frame caller leaves them asleep between frames) simply finds nothing
+    // left, so the call is never slower than the caller copying alone.
+    void copy2d(uint8_t *dst, size_t dpitch, const uint8_t *src, size_t spitch, size_t row, size_t nrows)
+    {
+        {
+            // a job is described under the mutex, and only once no worker is still inside the previous one
+            // (a worker that wakes up late must find either nothing to do or a completely described job)
+            std::unique_lock<std::mutex> lk(m_);
+            while (active_ > 0) { lk.unlock(); std::this_thread::yield(); lk.lock(); }
+            dst_ = dst; src_ = src; dpitch_ = dpitch; spitch_ = spitch; row_ = row; nrows_ = nrows;
+            rows_per_chunk_ = std::max<size_t>(1, (size_t)32768 / std::max<size_t>(row, 1));
+            nchunks_ = (int)((nrows + rows_per_chunk_ - 1) / rows_per_chunk_);
+            done_.store(0, std::memory_order_relaxed);
+            next_.store(0, std::memory_order_release);
+            if (!th_.empty() && nchunks_ > 4) gen_++;
+        }
+        if (!th_.empty() && nchunks_ > 4) cv_.notify_all();
+        run();
+        while (done_.load(std::memory_order_acquire) < nchunks_) std::this_thread::yield();
+    }
+
+private:
+    void run()
+    {
+        for (;;) {
+            const int c = next_.fetch_add(1, std::memory_order_acq_rel);
+            if (c >= nchunks_) return;
+            const size_t r0 = (size_t)c * rows_per_chunk_, r1 = std::min(nrows_, r0 + rows_per_chunk_);
+            if (dpitch_ == row_ && spitch_ == row_) memcpy(dst_ + r0 * row_, src_ + r0 * row_, (r1 - r0) * row_);
+            else
+                for (size_t r = r0; r < r1; r++) memcpy(dst_ + r * dpitch_, src_ + r * spitch_, row_);
+            done_.fetch_add(1, std::memory_order_acq_rel);
+        }
+    }
+    void worker()
+    {
+        unsigned seen = 0;
+        for (;;) {
+            {
+                std::unique_lock<std::mutex> lk(m_);
+                cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
+                if (stop_) return;
+                seen = gen_;
+                active_++;
+            }
+            run();
+            {
+                std::lock_guard<std::mutex> lk(m_);
+                active_--;
+            }
+        }
+    }
+    std::vector<std::thread> th_;
+    std::mutex m_;
+    std::condition_variable cv_;
+    unsigned gen_ = 0;
+    int active_ = 0; // workers inside run()
+    bool stop_ = false;
+    std::atomic<int> next_{0}, done_{0};
+    int nchunks_ = 0;
+    size_t rows_per_chunk_ = 1;
+    uint8_t *dst_ = nullptr;
+    const uint8_t *src_ = nullptr;
+    size_t dpitch_ = 0, spitch_ = 0, row_ = 0, nrows_ = 0;
+};
+
 struct FrameSlot {
+    uint8_t *h_stage = nullptr;   // page-locked staging of pageable host frames (allocated on first use)
     uint8_t *d_final = nullptr;   // final mask of the frame in this slot
     uint8_t *d_mask_det = nullptr; // detector output of the frame when a morphology chain follows
     BlobBuffers blobs = {};
@@ -136,7 +230,7 @@ struct gofpid_pipeline {
 
     size_t frames_pitch = 0, frames_stream = 0;
     const uint8_t *pinned_lo = nullptr, *pinned_hi = nullptr; // host range last found to be page-locked
-    uint8_t *h_frames = nullptr; // pinned staging for pageable input
+    HostCopier *copier = nullptr; // worker threads that move pageable frames into page-locked staging
     uint8_t *d_frames_base = nullptr; // device staging of all slots (slot i at i * frames_stream * n_streams)
 
     // a frame that exceeded the slot capacities, re-run with buffers of the size it needs (rerun_big)
@@ -277,7 +371,10 @@ void free_all(gofpid_pipeline *p)
         if (S.graph_b) cudaGraphDestroy(S.graph_b);
     }
     cudaFree(p->d_frames_base);
-    if (p->h_frames) cudaFreeHost(p->h_frames);
+    delete p->copier;
+    p->copier = nullptr;
+    for (auto &S : p->slots)
+        if (S.h_stage) cudaFreeHost(S.h_stage);
     for (auto &e : p->ev) if (e) cudaEventDestroy(e);
     for (cudaStream_t s : {p->stream, p->stream_c, p->stream_h})
         if (s) cudaStreamDestroy(s);
@@ -912,13 +1009,18 @@ int stage_host_frames(gofpid_pipeline *p, int ahead, const uint8_t *h_frames, si
     // stage A of the slot's previous frame must have finished reading the staging buffer
     if (F.used) GOFPID_CUDA_TRY(cudaStreamWaitEvent(sh, F.ev_mask, 0));
     if (!pinned) {
-        // pageable memory: stage through one pinned buffer (synchronous for the caller)
-        if (!p->h_frames) GOFPID_CUDA_TRY(cudaMallocHost(&p->h_frames, row * p->H * p->n_streams));
-        GOFPID_CUDA_TRY(cudaStreamSynchronize(sh)); // the previous copy out of h_frames is done
+        // pageable memory: through the slot's own page-locked buffer, filled by the copier threads; the
+        // upload of this frame then overlaps the filling of the next slot's buffer
+        if (!F.h_stage) GOFPID_CUDA_TRY(cudaMallocHost(&F.h_stage, row * p->H * p->n_streams));
+        if (!p->copier) {
+            const unsigned hc = std::thread::hardware_concurrency();
+            p->copier = new (std::nothrow) HostCopier((int)std::min(3u, hc > 1 ? hc - 1 : 0u));
+            if (!p->copier) { set_error("out of host memory"); return GOFPID_ERR_NOMEM; }
+        }
+        GOFPID_CUDA_TRY(cudaEventSynchronize(F.ev_h2d)); // the slot's previous upload out of h_stage is done
         for (int z = 0; z < p->n_streams; z++)
-            for (int y = 0; y < p->H; y++)
-                memcpy(p->h_frames + ((size_t)z * p->H + y) * row, h_frames + z * stream_stride + (size_t)y * pitch, row);
-        src = p->h_frames; spitch = row; sstride = row * p->H;
+            p->copier->copy2d(F.h_stage + (size_t)z * p->H * row, row, h_frames + z * stream_stride, pitch, row, (size_t)p->H);
+        src = F.h_stage; spitch = row; sstride = row * p->H;
     }
     if ((sstride == spitch * p->H || p->n_streams == 1) && spitch == row && p->frames_pitch == row) {
         // dense on both sides: one linear copy (a 2-D copy of the same bytes is described row by row)
@@ -1037,11 +1139,10 @@ int run_sequence(gofpid_pipeline *p, const uint8_t *frames, bool host, int n_fra
         return GOFPID_OK;
     };
     int staged = 0; // frames of this clip whose host->device copy has been issued
-    // Host clips are uploaded half a ring of frame slots at a time, ahead of the frames being enqueued:
-    // the copy of the next chunk only waits for the detector launches that read the slots' previous
-    // frames, so the copy engine stays busy with large transfers while the detector works on the
-    // chunk before.
-    const int chunk = std::max(1, p->depth / 2);
+    // (GOFPID_H2D_CHUNK frames per copy; default: the frames of one detector launch.  Half a ring of slots per
+    // copy -- 12 MB instead of 6 -- was measured 8 % SLOWER end to end although larger copies alone are
+    // faster on the link: the first detector launch of a chunk then waits for all of it)
+    const int chunk_cfg = p->tune.h2d_chunk;
     while (t < n_frames) {
         int g = 1;
         if (p->group > 1 && p->frames >= p->depth && p->use_graph) g = std::min(p->group, n_frames - t);
@@ -1050,7 +1151,8 @@ int run_sequence(gofpid_pipeline *p, const uint8_t *frames, bool host, int n_fra
         const uint8_t *ptr[MOG2_MAX_GROUP];
         while (host && staged < t + g) {
             const int s0 = (int)((p->frames + (staged - t)) % p->depth);
-            const int n = std::min(std::min(chunk, n_frames - staged), p->depth - s0); // (a copy does not wrap around the ring)
+            const int chunk = chunk_cfg > 0 ? std::min(chunk_cfg, p->depth / 2) : t + g - staged;
+            const int n = std::min(std::min(std::max(chunk, 1), n_frames - staged), p->depth - s0); // (a copy does not wrap around the ring)
             GOFPID_TRY(stage_host_group(p, staged - t, n, frames + (size_t)staged * frame_stride, frame_stride, pitch, stream_stride));
             staged += n;
         }
@@ -1523,7 +1625,12 @@ GOFPID_API int gofpid_pipeline_knn_model(gofpid_pipeline *p, int stream_idx, uin
             const size_t s = (size_t)y * PW + x, d = (size_t)y * W + x;
             if (h_samples)
                 for (int k = 0; k < 21; k++)
-                    for (int c = 0; c < ND; c++) h_samples[(d * 21 + k) * ND + c] = smp[((size_t)k * pe + s) * ND + c];
+                    for (int c = 0; c < ND; c++) {
+                        // gray: every group of four pixels is (v0 v1 v2 v3 | f0 f1 f2 f3); colour: (c0 c1 c2 flag) per pixel
+                        const size_t at = ND == 2 ? ((size_t)k * pe + (s & ~(size_t)3)) * 2 + 4 * c + (s & 3)
+                                                  : ((size_t)k * pe + s) * ND + c;
+                        h_samples[(d * 21 + k) * ND + c] = smp[at];
+                    }
             if (h_idx) { h_idx[d] = idx[s] & 7; h_idx[n + d] = (idx[s] >> 3) & 7; h_idx[2 * n + d] = (idx[s] >> 6) & 7; }
             if (h_nxt) { h_nxt[d] = nxt[s] & 255; h_nxt[n + d] = (nxt[s] >> 8) & 255; h_nxt[2 * n + d] = (nxt[s] >> 16) & 255; }
         }

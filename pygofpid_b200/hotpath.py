@@ -418,6 +418,8 @@ def _blob_dict(pts, point_offset, n_points, y1, a00, a10, a01, anchor):
 def blobs_from_records(recs, pts, anchor="bottom"):
     """blobs_ lists from one frame's slice of process_sequence's output (records: BLOB_DTYPE rows,
     pts: that frame's contour points; point_offset restarts at 0 for every frame)."""
+    if not isinstance(recs, np.ndarray):  # a ctypes array of gofpid_blob (HotPath.raw_blobs)
+        return [_blob_dict(pts, b.point_offset, b.n_points, b.y1, b.a00, b.a10, b.a01, anchor) for b in recs]
     return [_blob_dict(pts, int(b['point_offset']), int(b['n_points']), int(b['y1']), int(b['a00']), int(b['a10']),
                        int(b['a01']), anchor) for b in recs]
 
