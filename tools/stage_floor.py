@@ -8,7 +8,7 @@ import torch
 from pygofpid_b200 import HotPath
 from bench import WORKLOADS, morph_list, make_clip
 wl = WORKLOADS["1080p_mog2_open_close_blobs"]
-NCLIP = 24
+NCLIP = int(os.environ.get("FLOOR_NCLIP", "24"))  # 24 frames = 50 MB: the clip stays in L2; 72: it streams from HBM as in bench.py
 frames = make_clip(wl, NCLIP)
 dev = torch.from_numpy(frames).cuda()
 row, fb = 1920, 1920 * 1080
