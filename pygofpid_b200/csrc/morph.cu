@@ -635,6 +635,8 @@ morph_bits_kernel(MorphPlan plan, ImageU8 src, ImageU8 dst, uint32_t *bitimg, in
                     for (int b = 0; b < 16; b++)
                         if (hx + b >= 0 && hx + b < W) v[b >> 2] |= (uint32_t)row[hx + b] << (8 * (b & 3));
                 }
+                // (most of a foreground mask is background: sixteen zero bytes are zero bits in every plane)
+                if ((v[0] | v[1] | v[2] | v[3]) == 0u) continue;
 #pragma unroll
                 for (int l = 0; l < 3; l++)
                     if (l < nl) {
@@ -718,17 +720,19 @@ morph_bits_kernel(MorphPlan plan, ImageU8 src, ImageU8 dst, uint32_t *bitimg, in
             for (int l = 0; l < 3; l++)
                 if (l < nl) p[l] = (A[(size_t)l * G.plane + si] >> (16 * h)) & 0xffffu;
         }
-        uint32_t o[4];
+        uint32_t o[4] = {0u, 0u, 0u, 0u};
+        if (p[0] | p[1] | p[2]) { // (sixteen background pixels are sixteen zero bytes: nothing to spread)
 #pragma unroll
-        for (int q = 0; q < 4; q++) {
-            uint32_t v = spread4(p[0] >> (4 * q)) & lv4[0];
+            for (int q = 0; q < 4; q++) {
+                uint32_t v = spread4(p[0] >> (4 * q)) & lv4[0];
 #pragma unroll
-            for (int l = 1; l < 3; l++)
-                if (l < nl) {
-                    const uint32_t ml = spread4(p[l] >> (4 * q));
-                    v = (v & ~ml) | (ml & lv4[l]);
-                }
-            o[q] = v;
+                for (int l = 1; l < 3; l++)
+                    if (l < nl) {
+                        const uint32_t ml = spread4(p[l] >> (4 * q));
+                        v = (v & ~ml) | (ml & lv4[l]);
+                    }
+                o[q] = v;
+            }
         }
         uint8_t *row = dbase + (size_t)gy * dst.pitch;
         if (daligned && (size_t)gx + 16 <= dst.pitch) {
