@@ -44,6 +44,9 @@ struct Tuning {
     int morph_bytes = 0;  // GOFPID_MORPH_BYTES=1: byte morphology kernel inside the pipeline
     int knn_scalar = 0;   // GOFPID_KNN_SCALAR=1: general KNN kernel on gray frames too (tests)
     int runs_cap = -1;    // GOFPID_RUNS_CAP: run capacity of the shared-memory labeller (tests: force the fallback)
+    int copier_threads = -1; // GOFPID_COPIER_THREADS: worker threads staging pageable host frames (-1: default, by host threads per GPU)
+    int copier_stream = 1;   // GOFPID_COPIER_STREAM=0: plain memcpy instead of streaming stores into the staging buffer
+    int copier_spin_us = 500; // GOFPID_COPIER_SPIN_US: how long a worker polls for the next frame before it sleeps
     int h2d_chunk = 0;    // GOFPID_H2D_CHUNK: frames per host->device copy of a host clip (0: the frames of one detector launch)
     int mog2_smem_pad = 0; // GOFPID_MOG2_SMEM_PAD: extra dynamic shared memory per MOG2 CTA (caps the CTAs per SM: A/B measurements)
     int mog2_generic = 0; // GOFPID_MOG2_GENERIC=1: the generic MOG2 kernel even for ordinary parameters (tests)

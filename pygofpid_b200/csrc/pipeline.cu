@@ -13,11 +13,15 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <new>
 #include <thread>
 #include <vector>
+#if defined(__x86_64__)
+#include <emmintrin.h>
+#endif
 
 namespace gofpid {
 
@@ -52,6 +56,9 @@ Tuning read_tuning()
     t.mog2_generic = flag("GOFPID_MOG2_GENERIC", '1');
     t.mog2_smem_pad = num("GOFPID_MOG2_SMEM_PAD", 0, 65536, 0);
     t.h2d_chunk = num("GOFPID_H2D_CHUNK", 0, 16, 0);
+    t.copier_threads = num("GOFPID_COPIER_THREADS", 0, 64, -1);
+    t.copier_spin_us = num("GOFPID_COPIER_SPIN_US", 0, 1000000, 500);
+    t.copier_stream = num("GOFPID_COPIER_STREAM", 0, 1, 1);
     return t;
 }
 
@@ -78,11 +85,13 @@ constexpr int DEFAULT_DEPTH_MOG2 = 12, DEFAULT_DEPTH_MOG2_MANY = 8;
 // Pageable host frames (what cv.VideoCapture.read() hands to GOFPID.detect) have to pass through page-locked
 // memory before the copy engine can take them.  One thread moves 2 MB in about 200 us -- five times what the
 // frame then needs over the link -- so the rows of a frame are split over a few persistent worker threads
-// (fork / join per frame), and every frame slot has its own page-locked buffer so that filling the next one
-// overlaps the upload of the previous one.
+// (fork / join per frame; the workers keep polling for a while after a job so that a per-frame caller finds
+// them awake), a frame is uploaded strip by strip while it is still being copied, and every frame slot has
+// its own page-locked buffer so that filling the next one overlaps the upload of the previous one.
 class HostCopier {
 public:
-    explicit HostCopier(int workers)
+    static constexpr int MAX_STRIPS = 16;
+    HostCopier(int workers, int spin_us, bool streaming) : spin_us_(spin_us), streaming_(streaming)
     {
         for (int i = 0; i < workers; i++) th_.emplace_back([this] { worker(); });
     }
@@ -91,16 +100,22 @@ public:
         {
             std::lock_guard<std::mutex> lk(m_);
             stop_ = true;
+            gen_pub_.fetch_add(1, std::memory_order_release);
         }
         cv_.notify_all();
         for (auto &t : th_) t.join();
     }
     // nrows rows of `row` bytes, source rows spitch apart, destination rows dpitch apart.  The rows are cut
     // into chunks that the caller and whichever workers are awake take one after the other: a worker that
-    // wakes up late (a synchronous per-frame caller leaves them asleep between frames) simply finds nothing
-    // left, so the call is never slower than the caller copying alone.
-    void copy2d(uint8_t *dst, size_t dpitch, const uint8_t *src, size_t spitch, size_t row, size_t nrows)
+    // wakes up late simply finds nothing left, so the call is never slower than the caller copying alone.
+    // The chunks form `nstrips` consecutive strips of rows; on_strip(first_row, n_rows) is called by the
+    // CALLER's thread, strip by strip in order, as soon as every chunk of the strip has been copied -- the
+    // caller starts the strip's upload while the rest of the frame is still being copied.
+    template <class OnStrip>
+    void copy2d(uint8_t *dst, size_t dpitch, const uint8_t *src, size_t spitch, size_t row, size_t nrows, int nstrips,
+                OnStrip &&on_strip)
     {
+        bool wake;
         {
             // a job is described under the mutex, and only once no worker is still inside the previous one
             // (a worker that wakes up late must find either nothing to do or a completely described job)
@@ -109,40 +124,103 @@ public:
             dst_ = dst; src_ = src; dpitch_ = dpitch; spitch_ = spitch; row_ = row; nrows_ = nrows;
             rows_per_chunk_ = std::max<size_t>(1, (size_t)32768 / std::max<size_t>(row, 1));
             nchunks_ = (int)((nrows + rows_per_chunk_ - 1) / rows_per_chunk_);
-            done_.store(0, std::memory_order_relaxed);
+            nstrips = std::max(1, std::min(std::min(nstrips, (int)MAX_STRIPS), nchunks_));
+            chunks_per_strip_ = (nchunks_ + nstrips - 1) / nstrips;
+            nstrips_ = (nchunks_ + chunks_per_strip_ - 1) / chunks_per_strip_;
+            for (int k = 0; k < nstrips_; k++) strip_done_[k].store(0, std::memory_order_relaxed);
             next_.store(0, std::memory_order_release);
-            if (!th_.empty() && nchunks_ > 4) gen_++;
+            wake = !th_.empty() && nchunks_ > 4;
+            if (wake) { gen_++; gen_pub_.fetch_add(1, std::memory_order_release); }
         }
-        if (!th_.empty() && nchunks_ > 4) cv_.notify_all();
-        run();
-        while (done_.load(std::memory_order_acquire) < nchunks_) std::this_thread::yield();
+        if (wake) cv_.notify_all();
+        int issued = 0;
+        while (issued < nstrips_) {
+            const bool worked = take_chunk();
+            while (issued < nstrips_) {
+                const int c0 = issued * chunks_per_strip_, c1 = std::min(nchunks_, c0 + chunks_per_strip_);
+                if (strip_done_[issued].load(std::memory_order_acquire) < c1 - c0) break;
+                const size_t r0 = (size_t)c0 * rows_per_chunk_, r1 = std::min(nrows_, (size_t)c1 * rows_per_chunk_);
+                on_strip(r0, r1 - r0);
+                issued++;
+            }
+            if (!worked && issued < nstrips_) cpu_pause();
+        }
+    }
+    void copy2d(uint8_t *dst, size_t dpitch, const uint8_t *src, size_t spitch, size_t row, size_t nrows)
+    {
+        copy2d(dst, dpitch, src, spitch, row, nrows, 1, [](size_t, size_t) {});
     }
 
 private:
-    void run()
+    static void cpu_pause()
     {
-        for (;;) {
-            const int c = next_.fetch_add(1, std::memory_order_acq_rel);
-            if (c >= nchunks_) return;
-            const size_t r0 = (size_t)c * rows_per_chunk_, r1 = std::min(nrows_, r0 + rows_per_chunk_);
-            if (dpitch_ == row_ && spitch_ == row_) memcpy(dst_ + r0 * row_, src_ + r0 * row_, (r1 - r0) * row_);
-            else
-                for (size_t r = r0; r < r1; r++) memcpy(dst_ + r * dpitch_, src_ + r * spitch_, row_);
-            done_.fetch_add(1, std::memory_order_acq_rel);
+#if defined(__x86_64__) || defined(__i386__)
+        __builtin_ia32_pause();
+#else
+        std::this_thread::yield();
+#endif
+    }
+    // The staging buffer is written once and then read by the copy engine: streaming stores spare the
+    // read-for-ownership of every destination line (a third of the memory traffic of a plain memcpy).
+    void copy_bytes(uint8_t *d, const uint8_t *s, size_t n) const
+    {
+#if defined(__x86_64__)
+        if (streaming_ && n >= 256) {
+            size_t head = (16 - (reinterpret_cast<uintptr_t>(d) & 15)) & 15;
+            memcpy(d, s, head);
+            d += head; s += head; n -= head;
+            size_t i = 0;
+            for (; i + 64 <= n; i += 64) {
+                const __m128i a = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s + i));
+                const __m128i b = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s + i + 16));
+                const __m128i c = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s + i + 32));
+                const __m128i e = _mm_loadu_si128(reinterpret_cast<const __m128i *>(s + i + 48));
+                _mm_stream_si128(reinterpret_cast<__m128i *>(d + i), a);
+                _mm_stream_si128(reinterpret_cast<__m128i *>(d + i + 16), b);
+                _mm_stream_si128(reinterpret_cast<__m128i *>(d + i + 32), c);
+                _mm_stream_si128(reinterpret_cast<__m128i *>(d + i + 48), e);
+            }
+            memcpy(d + i, s + i, n - i);
+            _mm_sfence(); // (streaming stores are weakly ordered: before the chunk is reported done)
+            return;
         }
+#endif
+        memcpy(d, s, n);
+    }
+    bool take_chunk()
+    {
+        const int c = next_.fetch_add(1, std::memory_order_acq_rel);
+        if (c >= nchunks_) return false;
+        const size_t r0 = (size_t)c * rows_per_chunk_, r1 = std::min(nrows_, r0 + rows_per_chunk_);
+        if (dpitch_ == row_ && spitch_ == row_) copy_bytes(dst_ + r0 * row_, src_ + r0 * row_, (r1 - r0) * row_);
+        else
+            for (size_t r = r0; r < r1; r++) copy_bytes(dst_ + r * dpitch_, src_ + r * spitch_, row_);
+        strip_done_[c / chunks_per_strip_].fetch_add(1, std::memory_order_acq_rel);
+        return true;
     }
     void worker()
     {
-        unsigned seen = 0;
+        unsigned seen = 0, seen_pub = 0;
         for (;;) {
+            // A synchronous per-frame caller comes back every few hundred microseconds; waking a sleeping
+            // thread costs a good part of that.  So a worker keeps looking for the next job for spin_us_
+            // after its last one before it goes to sleep on the condition variable.
+            if (spin_us_ > 0) {
+                const auto t0 = std::chrono::steady_clock::now();
+                while (gen_pub_.load(std::memory_order_acquire) == seen_pub) {
+                    cpu_pause();
+                    if (std::chrono::steady_clock::now() - t0 > std::chrono::microseconds(spin_us_)) break;
+                }
+            }
             {
                 std::unique_lock<std::mutex> lk(m_);
                 cv_.wait(lk, [&] { return stop_ || gen_ != seen; });
                 if (stop_) return;
                 seen = gen_;
+                seen_pub = gen_pub_.load(std::memory_order_relaxed);
                 active_++;
             }
-            run();
+            while (take_chunk()) {}
             {
                 std::lock_guard<std::mutex> lk(m_);
                 active_--;
@@ -152,11 +230,15 @@ private:
     std::vector<std::thread> th_;
     std::mutex m_;
     std::condition_variable cv_;
+    const int spin_us_;
+    const bool streaming_;
     unsigned gen_ = 0;
-    int active_ = 0; // workers inside run()
+    std::atomic<unsigned> gen_pub_{0}; // gen_ (and stop_) for the spinning workers, outside the mutex
+    int active_ = 0; // workers inside a job
     bool stop_ = false;
-    std::atomic<int> next_{0}, done_{0};
-    int nchunks_ = 0;
+    std::atomic<int> next_{0};
+    std::atomic<int> strip_done_[MAX_STRIPS];
+    int nchunks_ = 0, nstrips_ = 1, chunks_per_strip_ = 1;
     size_t rows_per_chunk_ = 1;
     uint8_t *dst_ = nullptr;
     const uint8_t *src_ = nullptr;
@@ -1013,15 +1095,35 @@ int stage_host_frames(gofpid_pipeline *p, int ahead, const uint8_t *h_frames, si
     // stage A of the slot's previous frame must have finished reading the staging buffer
     if (F.used) GOFPID_CUDA_TRY(cudaStreamWaitEvent(sh, F.ev_mask, 0));
     if (!pinned) {
-        // pageable memory: through the slot's own page-locked buffer, filled by the copier threads; the
-        // upload of this frame then overlaps the filling of the next slot's buffer
+        // pageable memory: through the slot's own page-locked buffer, filled by the caller and the copier
+        // threads; the upload of this frame then overlaps the filling of the next slot's buffer
         if (!F.h_stage) GOFPID_CUDA_TRY(cudaMallocHost(&F.h_stage, row * p->H * p->n_streams));
         if (!p->copier) {
             const unsigned hc = std::thread::hardware_concurrency();
-            p->copier = new (std::nothrow) HostCopier((int)std::min(3u, hc > 1 ? hc - 1 : 0u));
+            // (default: the host threads that fall to this GPU, half of them left to the caller, at most 7)
+            int ngpu = 1;
+            if (cudaGetDeviceCount(&ngpu) != cudaSuccess || ngpu < 1) { cudaGetLastError(); ngpu = 1; }
+            const int dflt = std::max(1, std::min(7, (int)hc / (2 * ngpu) - 1));
+            const int want = p->tune.copier_threads >= 0 ? p->tune.copier_threads : dflt;
+            p->copier = new (std::nothrow) HostCopier(std::min(want, hc > 1 ? (int)hc - 1 : 0), p->tune.copier_spin_us,
+                                                      p->tune.copier_stream != 0);
             if (!p->copier) { set_error("out of host memory"); return GOFPID_ERR_NOMEM; }
         }
         GOFPID_CUDA_TRY(cudaEventSynchronize(F.ev_h2d)); // the slot's previous upload out of h_stage is done
+        if (p->n_streams == 1 && p->frames_pitch == row) {
+            // one dense frame: cut into strips, and a strip travels while the next ones are still being copied
+            // (a synchronous caller -- GOFPID.detect -- waits for copy + upload + step of every frame)
+            const int nstrips = row * p->H >= (1u << 20) ? 4 : 1;
+            cudaError_t err = cudaSuccess;
+            p->copier->copy2d(F.h_stage, row, h_frames, pitch, row, (size_t)p->H, nstrips, [&](size_t r0, size_t nr) {
+                if (err == cudaSuccess)
+                    err = cudaMemcpyAsync(F.d_frames + r0 * row, F.h_stage + r0 * row, nr * row, cudaMemcpyHostToDevice, sh);
+            });
+            GOFPID_CUDA_TRY(err);
+            GOFPID_CUDA_TRY(cudaEventRecord(F.ev_h2d, sh));
+            GOFPID_CUDA_TRY(cudaStreamWaitEvent(p->stream, F.ev_h2d, 0));
+            return GOFPID_OK;
+        }
         for (int z = 0; z < p->n_streams; z++)
             p->copier->copy2d(F.h_stage + (size_t)z * p->H * row, row, h_frames + z * stream_stride, pitch, row, (size_t)p->H);
         src = F.h_stage; spitch = row; sstride = row * p->H;

@@ -1,0 +1,7 @@
+mkdir -p gpurun_out/r2y
+nproc
+for V in "" "GOFPID_COPIER_STREAM=0" "GOFPID_COPIER_THREADS=3" "GOFPID_COPIER_THREADS=3 GOFPID_COPIER_STREAM=0" "GOFPID_COPIER_THREADS=0"; do
+  echo "== $V"; env $V timeout 300 python tools/latency_breakdown.py 2>&1 | grep -E "pageable"
+  env $V timeout 300 python tools/dropin_rate.py 2>&1 | tail -1
+done 2>&1 | tee gpurun_out/r2y/latency.txt
+timeout 900 python -m pytest tests -m gpu -x -q -k "dropin or host or clip or pageable or pinned" > gpurun_out/r2y/pytest.log 2>&1; echo "pytest rc=$?"; tail -n 3 gpurun_out/r2y/pytest.log

@@ -4,9 +4,11 @@ dynamic opcode mix and the blocks of SASS that execute together with their share
 
     python tools/ncu_summary.py <report.ncu-rep> [warps (x frames) per launch, to print instructions per warp(-frame)] [min share]
 
-(the first kernel of the report; capture one kernel per report with -k / -c)"""
-import csv, collections, re, sys, subprocess
-rep=sys.argv[1]; warps_per_frame=float(sys.argv[2]) if len(sys.argv)>2 else 1
+(the first kernel of the report, or the first one whose name matches the regex in NCU_KERNEL)"""
+import csv, collections, os, re, sys, subprocess
+rep=sys.argv[1]
+if os.environ.get("NCU_KERNEL"): rep += " -k regex:%s -c 1" % os.environ["NCU_KERNEL"]
+warps_per_frame=float(sys.argv[2]) if len(sys.argv)>2 else 1
 subprocess.run(f"ncu -i {rep} --page source --csv > /tmp/_src.csv 2>/dev/null; ncu -i {rep} --page raw --csv > /tmp/_raw.csv 2>/dev/null",shell=True)
 rows=list(csv.reader(open('/tmp/_raw.csv')))
 h=rows[0]; r=rows[2]
