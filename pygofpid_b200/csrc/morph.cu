@@ -522,17 +522,30 @@ struct BitItem {
 };
 
 // One step for one work item: output rows r0 .. r0+MB_R-1 of word column w.
+// Returns the OR of the in-image bits it wrote (0: the item's output is empty).
 template <bool DIL, int K>
-__device__ __forceinline__ void op_item(const MorphOpDev &op, const MorphRun *__restrict__ runs,
-                                        const uint32_t *A, uint32_t *B, const BitItem &it, const BitGeom &G,
-                                        int NWP, uint32_t ident_next)
+__device__ __forceinline__ uint32_t op_item(const MorphOpDev &op, const MorphRun *__restrict__ runs,
+                                            const uint32_t *A, uint32_t *B, const BitItem &it, const BitGeom &G,
+                                            int NWP, uint32_t ident_next, bool anchored)
 {
     const uint32_t ident = DIL ? 0u : 0xffffffffu;
     const uint32_t *Ap = A + it.base;
     uint32_t acc[MB_R];
 #pragma unroll
     for (int q = 0; q < MB_R; q++) acc[q] = ident;
-    if (K > 0) {
+    bool skip = false;
+    if (!DIL && anchored) {
+        // an erosion whose structuring element holds its anchor only removes pixels: where the item's own
+        // words are empty (most of a detector's mask, and its salt noise dies here) so is its output
+        uint32_t own = 0u;
+#pragma unroll
+        for (int q = 0; q < MB_R; q++) own |= Ap[q * NWP];
+        skip = own == 0u;
+    }
+    if (skip) {
+#pragma unroll
+        for (int q = 0; q < MB_R; q++) acc[q] = 0u;
+    } else if (K > 0) {
         // K x K rectangle: K + MB_R - 1 row windows, each output row is the AND / OR of K of them
         constexpr int KK = K > 0 ? K : 1;
         uint32_t h[MB_R + KK - 1];
@@ -567,25 +580,28 @@ __device__ __forceinline__ void op_item(const MorphOpDev &op, const MorphRun *__
     }
     // cells outside the image take the identity of the NEXT step (OpenCV ignores them)
     uint32_t *Bp = B + it.base;
+    uint32_t nz = 0u;
 #pragma unroll
     for (int q = 0; q < MB_R; q++) {
         const int r = it.r0 + q;
         if (r >= G.rows) break;
         const int gy = G.gy0 + r;
         const uint32_t m = (gy >= 0 && gy < G.H) ? it.inm : 0u;
+        nz |= acc[q] & m;
         Bp[q * NWP] = (acc[q] & m) | (ident_next & ~m);
     }
+    return nz;
 }
 
 template <bool DIL>
-__device__ __forceinline__ void op_item_dispatch(const MorphOpDev &op, const MorphRun *__restrict__ runs,
-                                                 const uint32_t *A, uint32_t *B, const BitItem &it,
-                                                 const BitGeom &G, int NWP, uint32_t ident_next)
+__device__ __forceinline__ uint32_t op_item_dispatch(const MorphOpDev &op, const MorphRun *__restrict__ runs,
+                                                     const uint32_t *A, uint32_t *B, const BitItem &it,
+                                                     const BitGeom &G, int NWP, uint32_t ident_next, bool anchored)
 {
     const bool sq = op.is_rect && op.kw == op.kh && (op.kw & 1);
-    if (sq && op.kw == 5) op_item<DIL, 5>(op, runs, A, B, it, G, NWP, ident_next);
-    else if (sq && op.kw == 3) op_item<DIL, 3>(op, runs, A, B, it, G, NWP, ident_next);
-    else op_item<DIL, 0>(op, runs, A, B, it, G, NWP, ident_next);
+    if (sq && op.kw == 5) return op_item<DIL, 5>(op, runs, A, B, it, G, NWP, ident_next, anchored);
+    if (sq && op.kw == 3) return op_item<DIL, 3>(op, runs, A, B, it, G, NWP, ident_next, anchored);
+    return op_item<DIL, 0>(op, runs, A, B, it, G, NWP, ident_next, anchored);
 }
 
 __global__ void __launch_bounds__(MB_THREADS)
@@ -654,7 +670,7 @@ morph_bits_kernel(MorphPlan plan, ImageU8 src, ImageU8 dst, uint32_t *bitimg, in
             if (l < nl) A[(size_t)l * G.plane + cell] = (bits[l] & m) | (ident0 & ~m);
         any |= (bits[0] & m) != 0u;
     }
-    const bool nonempty = __syncthreads_or(any) || !plan.anchored;
+    bool nonempty = __syncthreads_or(any) || !plan.anchored;
 
     const int tile_h = plan.bit_tile_h;
     if (nonempty) {
@@ -682,12 +698,14 @@ morph_bits_kernel(MorphPlan plan, ImageU8 src, ImageU8 dst, uint32_t *bitimg, in
             const uint32_t ident_next =
                 (k + 1 < plan.n_ops && plan.ops[k + 1].op == GOFPID_MORPH_ERODE) ? 0xffffffffu : 0u;
             const bool dil = op.op == GOFPID_MORPH_DILATE;
+            const bool anch = plan.anchored != 0;
+            uint32_t nz = 0u;
             if (small) {
 #pragma unroll
                 for (int q = 0; q < MB_MAXI; q++)
                     if (q < n_mine) {
-                        if (dil) op_item_dispatch<true>(op, plan.d_runs, A, B, items[q], G, NWP, ident_next);
-                        else op_item_dispatch<false>(op, plan.d_runs, A, B, items[q], G, NWP, ident_next);
+                        if (dil) nz |= op_item_dispatch<true>(op, plan.d_runs, A, B, items[q], G, NWP, ident_next, anch);
+                        else nz |= op_item_dispatch<false>(op, plan.d_runs, A, B, items[q], G, NWP, ident_next, anch);
                     }
             } else {
                 for (int item = tid; item < nitems; item += MB_THREADS) {
@@ -696,12 +714,15 @@ morph_bits_kernel(MorphPlan plan, ImageU8 src, ImageU8 dst, uint32_t *bitimg, in
                     const int rb = t % nrb, l = t / nrb;
                     it.w = w; it.r0 = rb * MB_R; it.base = l * G.plane + org + rb * MB_R * NWP + w;
                     it.inm = in_image_bits(G, w);
-                    if (dil) op_item_dispatch<true>(op, plan.d_runs, A, B, it, G, NWP, ident_next);
-                    else op_item_dispatch<false>(op, plan.d_runs, A, B, it, G, NWP, ident_next);
+                    if (dil) nz |= op_item_dispatch<true>(op, plan.d_runs, A, B, it, G, NWP, ident_next, anch);
+                    else nz |= op_item_dispatch<false>(op, plan.d_runs, A, B, it, G, NWP, ident_next, anch);
                 }
             }
-            __syncthreads();
+            // (the barrier between two steps also tells whether anything is left: the salt noise of a
+            // detector's mask is gone after the first erosion, and an empty tile stays empty)
+            const bool left = __syncthreads_or(nz != 0u) != 0;
             uint32_t *t = A; A = B; B = t;
+            if (!left && anch) { nonempty = false; break; }
         }
     }
     // (an empty tile -- no foreground anywhere the chain can see -- stays empty through a chain of
