@@ -74,6 +74,9 @@ WORKLOADS = {
     # configs[4]
     "1080p_knn_many_blobs": dict(H=1080, W=1920, C=1, detector="KNN", n_obj=400, seed=5, clip=72, passes=6,
                                  obj_size=(12, 90, 8, 80), morph=[("erode", 5), ("dilate", 5)]),
+    # (not a BASELINE configuration: the colour KNN kernel for profiles/)
+    "1080p_bgr_knn": dict(H=1080, W=1920, C=3, detector="KNN", n_obj=12, seed=6, clip=24, passes=4,
+                          morph=[("erode", 5), ("dilate", 5)]),
 }
 DEFAULT_WORKLOAD = "1080p_mog2_open_close_blobs"
 EXTRA_CONFIGS = ["320x240_fd_open_blobs", "1080p_bgr_mog2_open_close_blobs", "4k_mog2_ellipse15_open_blobs",
@@ -459,7 +462,7 @@ def roofline_obj(name, wl, m):
     H, W, C = wl["H"], wl["W"], wl["C"]
     if wl["detector"] == "MOG2":
         bpp = C + 2.0 * (1 + m["nbar"] * 4 * (2 + C)) + 1
-        kname = "mog2_kernel"
+        kname = "mog2_lean_kernel"  # (default MOG2 parameters are "ordinary": launch_mog2 takes the lean kernel)
     elif wl["detector"] == "KNN":
         bpp = C + 21 * (C + 1) + 6 + 1
         kname = "knn_gray_kernel" if C == 1 else "knn_kernel"
