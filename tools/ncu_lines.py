@@ -14,8 +14,8 @@ for r in rows[:hdr]:
     if r and r[0] == "File Path": cur_file = os.path.basename(r[1])
 tot = 0
 for r in rows[hdr + 1:]:
-    if len(r) <= ie: continue
     if r and r[0] == "File Path": cur_file = os.path.basename(r[1]); continue
+    if len(r) <= ie: continue
     if r[0].isdigit():
         try: e = int(r[ie]); sm = int(r[isamp])
         except ValueError: continue
