@@ -1121,7 +1121,6 @@ int stage_host_frames(gofpid_pipeline *p, int ahead, const uint8_t *h_frames, si
             });
             GOFPID_CUDA_TRY(err);
             GOFPID_CUDA_TRY(cudaEventRecord(F.ev_h2d, sh));
-            GOFPID_CUDA_TRY(cudaStreamWaitEvent(p->stream, F.ev_h2d, 0));
             return GOFPID_OK;
         }
         for (int z = 0; z < p->n_streams; z++)
@@ -1140,8 +1139,7 @@ int stage_host_frames(gofpid_pipeline *p, int ahead, const uint8_t *h_frames, si
                                               src + z * sstride, spitch, row, p->H, cudaMemcpyHostToDevice, sh));
     }
     GOFPID_CUDA_TRY(cudaEventRecord(F.ev_h2d, sh));
-    GOFPID_CUDA_TRY(cudaStreamWaitEvent(p->stream, F.ev_h2d, 0));
-    return GOFPID_OK;
+    return GOFPID_OK; // (the caller makes the detector's stream wait for F.ev_h2d when the frame's turn comes)
 }
 
 // g consecutive frames of a dense pinned clip -> g consecutive slots (starting `ahead` slots after the
@@ -1178,9 +1176,7 @@ int stage_host_group(gofpid_pipeline *p, int ahead, int g, const uint8_t *h_fram
     else
         GOFPID_CUDA_TRY(cudaMemcpy2DAsync(p->slots[s0].d_frames, p->frames_pitch, h_frames, pitch, row,
                                           (size_t)p->H * p->n_streams * g, cudaMemcpyHostToDevice, sh));
-    FrameSlot &L = p->slots[s0 + g - 1];
-    GOFPID_CUDA_TRY(cudaEventRecord(L.ev_h2d, sh));
-    GOFPID_CUDA_TRY(cudaStreamWaitEvent(p->stream, L.ev_h2d, 0));
+    for (int f = 0; f < g; f++) GOFPID_CUDA_TRY(cudaEventRecord(p->slots[s0 + f].ev_h2d, sh)); // (every slot: groups and copies need not align)
     return GOFPID_OK;
 }
 
@@ -1189,6 +1185,7 @@ int submit_host(gofpid_pipeline *p, const uint8_t *h_frames, size_t pitch, size_
 {
     GOFPID_TRY(stage_host_frames(p, 0, h_frames, pitch, stream_stride));
     FrameSlot &F = p->slots[p->frames % p->depth];
+    GOFPID_CUDA_TRY(cudaStreamWaitEvent(p->stream, F.ev_h2d, 0));
     p->from_host = true;
     const int rc = run_step(p, F.d_frames, p->frames_pitch, p->frames_stream, p->stream);
     p->from_host = false;
@@ -1245,23 +1242,32 @@ int run_sequence(gofpid_pipeline *p, const uint8_t *frames, bool host, int n_fra
         return GOFPID_OK;
     };
     int staged = 0; // frames of this clip whose host->device copy has been issued
-    // (GOFPID_H2D_CHUNK frames per copy; default: the frames of one detector launch.  Half a ring of slots per
-    // copy -- 12 MB instead of 6 -- was measured 8 % SLOWER end to end although larger copies alone are
-    // faster on the link: the first detector launch of a chunk then waits for all of it)
+    // Uploads run AHEAD of the step: the copy of a frame only needs its slot's staging buffer, which is free
+    // once stage A of the slot's previous frame has run (a wait on the copy stream), not that frame's blob
+    // lists -- so the copies of the next group(s) are queued BEFORE the host blocks collecting old results,
+    // and the copy engine, which bounds the end-to-end rate, never runs dry (measured: 42.4 -> 39.x us per
+    // 1080p frame against 39.0 for the copies alone).  GOFPID_H2D_CHUNK frames per copy; default: the frames
+    // of one detector launch (half a ring of slots per copy was measured 8 % SLOWER: the first detector
+    // launch of a chunk then waits for all of it).
     const int chunk_cfg = p->tune.h2d_chunk;
+    const int per_copy = std::max(1, chunk_cfg > 0 ? std::min(chunk_cfg, p->depth / 2) : p->group);
+    const int lead = std::min(2 * per_copy, p->depth / 2); // frames staged beyond the group about to run
     while (t < n_frames) {
         int g = 1;
         if (p->group > 1 && p->frames >= p->depth && p->use_graph) g = std::min(p->group, n_frames - t);
-        // frames t .. t+g-1 take the slots of frames t-depth .. t+g-1-depth: collect those first
-        if (h_counts) GOFPID_TRY(collect(t + g - 1 - p->depth));
         const uint8_t *ptr[MOG2_MAX_GROUP];
-        while (host && staged < t + g) {
+        // (frame u goes into the slot of frame u - depth, whose stage A has been submitted when u - depth < t)
+        while (host && staged < std::min(n_frames, std::min(t + g + lead, t + p->depth))) {
             const int s0 = (int)((p->frames + (staged - t)) % p->depth);
-            const int chunk = chunk_cfg > 0 ? std::min(chunk_cfg, p->depth / 2) : t + g - staged;
-            const int n = std::min(std::min(std::max(chunk, 1), n_frames - staged), p->depth - s0); // (a copy does not wrap around the ring)
+            int n = std::min(std::min(per_copy, n_frames - staged), p->depth - s0); // (a copy does not wrap around the ring)
+            n = std::min(n, t + p->depth - staged);
+            if (staged < t + g) n = std::min(n, t + g - staged); // (the group about to run: no more than it needs)
             GOFPID_TRY(stage_host_group(p, staged - t, n, frames + (size_t)staged * frame_stride, frame_stride, pitch, stream_stride));
             staged += n;
         }
+        // frames t .. t+g-1 take the slots of frames t-depth .. t+g-1-depth: collect those first
+        if (h_counts) GOFPID_TRY(collect(t + g - 1 - p->depth));
+        if (host) GOFPID_CUDA_TRY(cudaStreamWaitEvent(p->stream, p->slots[(p->frames + g - 1) % p->depth].ev_h2d, 0));
         for (int f = 0; f < g; f++)
             ptr[f] = host ? p->slots[(p->frames + f) % p->depth].d_frames : frames + (size_t)(t + f) * frame_stride;
         p->from_host = host;

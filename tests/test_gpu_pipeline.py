@@ -80,6 +80,33 @@ def test_mog2_masks_and_model_bitexact(H, W, C, sigma, generic, monkeypatch):
     assert abs(hp.mog2_mean_modes() - ok.mean()) < 1e-9
 
 
+@pytest.mark.parametrize("det,C", [("MOG2", 1), ("MOG2", 3), ("KNN", 1)])
+@pytest.mark.parametrize("H,W", [(2, 8), (9, 68), (16, 64), (24, 132), (17, 260), (8, 12)])
+def test_register_blur_on_border_tiles(det, C, H, W):
+    """3x3 Gaussian evaluated in registers on EVERY tile of frames that are a whole number of words wide:
+    reflected rows (H = 2: both neighbours of a row are the other row), reflected pixels at both borders, a
+    last tile with a single valid lane (W = 68: that lane loads its left neighbour and reflects on the right),
+    lanes and rows of a tile outside the frame -- masks of a few frames against the oracle on the oracle's blur."""
+    blur = ("gaussian", (3, 3), 4.0)
+    seed = 4242
+    hp = _hot(_shape(H, W, C), blur=blur, detector=det, morph=(), find_blobs=False, knn_seed=seed)
+    ora = cport.MOG2(H, W, C) if det == "MOG2" else cport.KNN(H, W, C, seed)
+    rng = np.random.default_rng(H * 1000 + W + C)
+    base = rng.integers(0, 256, size=_shape(H, W, C), dtype=np.uint8)
+    for t in range(12):
+        f = base.copy()
+        if t % 3 == 2:  # a frame that differs everywhere: every pixel leaves the matched-background path
+            f = rng.integers(0, 256, size=_shape(H, W, C), dtype=np.uint8)
+        else:
+            f = (f.astype(np.int16) + rng.integers(-3, 4, size=f.shape)).clip(0, 255).astype(np.uint8)
+        b = cport.gaussian_blur(f, blur[1], blur[2]).reshape(f.shape)
+        want = ora.apply(b)
+        hp.process(f)
+        got = hp.mask()
+        assert np.array_equal(got, want), (det, C, H, W, t, int((got != want).sum()))
+    hp.close()
+
+
 @pytest.mark.parametrize("blur", [("gaussian", (3, 3), 4.0), ("gaussian", (3, 3), 0.0), ("box", (3, 3)),
                                   ("gaussian", (3, 3), 0.05)])
 @pytest.mark.parametrize("H,W", [(40, 260), (41, 331)])
