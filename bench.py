@@ -74,6 +74,9 @@ WORKLOADS = {
     # configs[4]
     "1080p_knn_many_blobs": dict(H=1080, W=1920, C=1, detector="KNN", n_obj=400, seed=5, clip=72, passes=6,
                                  obj_size=(12, 90, 8, 80), morph=[("erode", 5), ("dilate", 5)]),
+    # (not a BASELINE configuration: KNN on the headline scene -- a dozen objects over a static background)
+    "1080p_knn_few_blobs": dict(H=1080, W=1920, C=1, detector="KNN", n_obj=12, seed=2, clip=72, passes=6,
+                                morph=[("erode", 5), ("dilate", 5)]),
     # (not a BASELINE configuration: the colour KNN kernel for profiles/)
     "1080p_bgr_knn": dict(H=1080, W=1920, C=3, detector="KNN", n_obj=12, seed=6, clip=24, passes=4,
                           morph=[("erode", 5), ("dilate", 5)]),
