@@ -63,7 +63,7 @@ WORKLOADS = {
     "1080p_bgr_mog2_open_close_blobs": dict(H=1080, W=1920, C=3, detector="MOG2", n_obj=12, seed=2, clip=24, passes=32,
                                             morph=[("erode", 5), ("dilate", 5), ("dilate", 5), ("erode", 5)]),
     # configs[0]
-    "320x240_fd_open_blobs": dict(H=240, W=320, C=1, detector="FD", n_obj=6, seed=1, clip=72, passes=40,
+    "320x240_fd_open_blobs": dict(H=240, W=320, C=1, detector="FD", n_obj=6, seed=1, clip=1728, passes=2,
                                   morph=[("erode", 3), ("dilate", 3)]),
     # configs[2]
     "4k_mog2_ellipse15_open_blobs": dict(H=2160, W=3840, C=1, detector="MOG2", n_obj=16, seed=3, clip=18, passes=24,
@@ -118,7 +118,11 @@ def make_streams(wl, n_frames, streams):
 def config_of(name, wl, S, world):
     """The `config` object: identical for both arms of the same workload."""
     F = wl["clip"] * wl["passes"]
-    return {"workload": name, "shape": [wl["H"], wl["W"], wl["C"]], "detector": wl["detector"],
+    clip_mb = wl["clip"] * S * wl["H"] * wl["W"] * wl["C"] / 1e6
+    l2 = ("inputs larger than L2: every pass streams a %.0f MB clip per GPU (L2 is 126 MB), no flush needed" % clip_mb
+          if clip_mb > 126 else
+          "the %.1f MB clip of this frame size stays in the 126 MB L2 (no flush: frames this small are L2-resident)" % clip_mb)
+    return {"workload": name, "l2": l2, "shape": [wl["H"], wl["W"], wl["C"]], "detector": wl["detector"],
             "blur": "gaussian3x3_sigma4", "morph": ["%s%s" % (op, k) for op, k in wl["morph"]], "area_min": 100,
             "streams_per_gpu": S, "clip_frames": wl["clip"], "passes_per_step": wl["passes"], "frames_per_step": F * S}
 
