@@ -119,7 +119,7 @@ typedef struct gofpid_config {
 
     /* pipelining; 0 = default.  A synchronous caller (GOFPID.detect: one frame per call) never has
      * more than one frame in flight and may ask for a shallow handle to save memory. */
-    int32_t depth;         /* frame slots = frames that can be in flight (1 .. 16; default 6, MOG2 12) */
+    int32_t depth;         /* frame slots = frames that can be in flight (1 .. 16; default 12, 4 - 8 with many streams) */
     int32_t mog2_group;    /* frames per MOG2 launch in the clip entry points (1 .. 8; default 3)   */
 } gofpid_config;
 
