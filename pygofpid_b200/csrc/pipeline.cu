@@ -66,9 +66,9 @@ Tuning read_tuning()
 
 using namespace gofpid;
 
-// Up to DEPTH frames are in flight: stage A (tick, blur+detect, morphology) of frame t+1 runs on
-// the caller's stream while stage B (run extraction, labelling, border tracing) of frames t and
-// t-1 runs on the internal streams of their slots.  The temporal model makes stage A strictly
+// Up to DEPTH frames are in flight: stage A (tick, blur+detect) of frame t+1 runs on the caller's
+// stream while stage B (morphology, run extraction, labelling, border tracing, results) of the
+// frames before it runs on the internal streams of their slots.  The temporal model makes stage A strictly
 // sequential; stage B only needs the finished mask of its own frame and occupies a handful of
 // SMs (one CTA per stream or per blob), so consecutive frames of ONE camera stream overlap and
 // the frame rate is set by stage A alone.

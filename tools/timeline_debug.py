@@ -1,5 +1,6 @@
 """Debug aid: when do stage A (detector) and stage B (morphology .. blobs) of every frame slot end,
-relative to a mark on the launch stream?  GOFPID_MOG2_GROUP / GOFPID_DEPTH as usual."""
+relative to a mark on the launch stream?  GOFPID_MOG2_GROUP / GOFPID_DEPTH as usual.  Needs the debug
+build, which alone exports gofpid_debug_*: `make -C pygofpid_b200/csrc debug`, then GOFPID_LIB=libgofpid_b200_dbg.so."""
 import os, sys
 import ctypes as ct
 os.environ["GOFPID_EVENT_TIMING"] = "1"
