@@ -372,9 +372,9 @@ def measure(name, wl, S, streams, steps, warmup, local, dist, world, e2e_per_fra
     # ---- end to end through the clip entry point: pinned host frames in, blob lists out ----------
     # One library call per host clip.  A call fills and drains the frame pipeline once, so the clip handed over
     # is the 72-frame clip several times over (what a caller decoding a file in chunks would pass), as many
-    # passes per call as fit in ~600 MB of pinned memory.
+    # passes per call as fit in ~1.2 GB of pinned memory.
     e2e_steps = max(1, steps // 4)
-    per_call = max(1, min(passes, int(6e8 // max(pinned.numel(), 1))))
+    per_call = max(1, min(passes, int(1.2e9 // max(pinned.numel(), 1))))
     while passes % per_call:
         per_call -= 1
     long_clip = pinned if per_call == 1 else torch.cat([pinned] * per_call).pin_memory()
