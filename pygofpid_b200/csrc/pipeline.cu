@@ -19,6 +19,7 @@
 #include <new>
 #include <thread>
 #include <vector>
+#include <nvtx3/nvToolsExt.h>
 #if defined(__x86_64__)
 #include <emmintrin.h>
 #endif
@@ -65,6 +66,17 @@ Tuning read_tuning()
 } // namespace gofpid
 
 using namespace gofpid;
+
+// NVTX ranges around the host side of a step (visible in nsys / `ncu --nvtx`; a few nanoseconds each when no
+// tool is attached): uploads, the enqueue of stage A + stage B, result collection, re-runs of overflowed frames.
+namespace {
+struct NvtxRange {
+    explicit NvtxRange(const char *name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange &) = delete;
+    NvtxRange &operator=(const NvtxRange &) = delete;
+};
+} // namespace
 
 // Up to DEPTH frames are in flight: stage A (tick, blur+detect) of frame t+1 runs on the caller's
 // stream while stage B (morphology, run extraction, labelling, border tracing, results) of the
@@ -752,6 +764,7 @@ int build_graphs(gofpid_pipeline *p, FrameSlot &F, const FrameSrc &src)
 int run_step(gofpid_pipeline *p, const uint8_t *d_frames, size_t pitch, size_t stream_stride,
              cudaStream_t s)
 {
+    NvtxRange nvtx_range("gofpid: step (stage A + stage B enqueue)");
     const FrameSrc src{d_frames, pitch, stream_stride};
     FrameSlot &F = p->slots[p->frames % p->depth];
     int la = 0, lb = 0;
@@ -819,6 +832,7 @@ int run_step(gofpid_pipeline *p, const uint8_t *d_frames, size_t pitch, size_t s
 int run_group(gofpid_pipeline *p, const uint8_t *const *frames, int g, size_t pitch, size_t stream_stride,
               cudaStream_t s)
 {
+    NvtxRange nvtx_range("gofpid: frame group (MOG2 launch + stage Bs)");
     if (g == 1 || p->cfg.detector != GOFPID_DETECT_MOG2 || !p->use_graph || p->frames < p->depth ||
         g > p->depth || g > MOG2_MAX_GROUP) {
         for (int f = 0; f < g; f++) GOFPID_TRY(run_step(p, frames[f], pitch, stream_stride, s));
@@ -894,6 +908,7 @@ int run_group(gofpid_pipeline *p, const uint8_t *const *frames, int g, size_t pi
 // Brings the per-stream headers, kept blobs and contour points of a slot's frame to the host.
 int fetch_results(gofpid_pipeline *p, FrameSlot *F)
 {
+    NvtxRange nvtx_range("gofpid: wait for a frame's results");
     if (!F) { set_error("no frame has been processed yet"); return GOFPID_ERR_INVALID; }
     if (F->fetched) return GOFPID_OK;
     const int S = p->n_streams;
@@ -916,6 +931,7 @@ int fetch_results(gofpid_pipeline *p, FrameSlot *F)
 // points exactly -- while the temporal model is untouched.  Rare and synchronous.
 int rerun_big(gofpid_pipeline *p, FrameSlot *F, int z)
 {
+    NvtxRange nvtx_range("gofpid: re-run blob creation with larger buffers");
     if (p->big.slot == F && p->big.frame_index == F->frame_index && p->big.stream == z) return GOFPID_OK;
     p->big.slot = nullptr;
     const int H = p->H, W = p->W;
@@ -1062,6 +1078,7 @@ int ordered_blobs(gofpid_pipeline *p, FrameSlot *F, int z, gofpid_blob *h_blobs,
 // the source is pinned).
 int stage_host_frames(gofpid_pipeline *p, int ahead, const uint8_t *h_frames, size_t pitch, size_t stream_stride)
 {
+    NvtxRange nvtx_range("gofpid: upload frame");
     const size_t row = (size_t)p->W * p->Csrc;
     if (pitch < row) { set_error("pitch %zu smaller than a row (%zu bytes)", pitch, row); return GOFPID_ERR_INVALID; }
     FrameSlot &F = p->slots[(p->frames + ahead) % p->depth];
@@ -1149,6 +1166,7 @@ int stage_host_frames(gofpid_pipeline *p, int ahead, const uint8_t *h_frames, si
 int stage_host_group(gofpid_pipeline *p, int ahead, int g, const uint8_t *h_frames, size_t frame_stride, size_t pitch,
                      size_t stream_stride)
 {
+    NvtxRange nvtx_range("gofpid: upload frame group");
     const size_t row = (size_t)p->W * p->Csrc;
     const int s0 = (int)((p->frames + ahead) % p->depth);
     bool one = g > 1 && s0 + g <= p->depth && p->d_frames_base && pitch >= row &&
@@ -1200,6 +1218,7 @@ int run_sequence(gofpid_pipeline *p, const uint8_t *frames, bool host, int n_fra
                  size_t pitch, size_t stream_stride, cudaStream_t s, gofpid_blob *h_blobs, int blob_capacity,
                  int32_t *h_points, int point_capacity, int32_t *h_counts)
 {
+    NvtxRange nvtx_range("gofpid: clip");
     const int S = p->n_streams;
     long nb_total = 0, np_total = 0;
     int t = 0, c = 0; // frames of this clip submitted / collected
