@@ -164,6 +164,13 @@ GOFPID_API void gofpid_config_default(gofpid_config *cfg);
  * the CPU to read back: fill it, do not read it).  Free with gofpid_host_free. */
 GOFPID_API int gofpid_host_alloc(size_t bytes, int write_combined, void **out);
 GOFPID_API int gofpid_host_free(void *ptr);
+/* Copies n_rows rows of row_bytes bytes between HOST buffers with the library's staging threads (the ones
+ * that move pageable frames into page-locked memory inside the host entry points; streaming stores): for
+ * capture loops that fill a gofpid_host_alloc buffer themselves -- one thread moves a 1080p frame in
+ * 170-240 us, the link needs 40.  n_threads: worker threads beside the caller (0: the caller alone,
+ * < 0: default).  Pure host code, no CUDA call; one copy at a time per process. */
+GOFPID_API int gofpid_host_copy2d(void *dst, size_t dst_pitch, const void *src, size_t src_pitch,
+                                  size_t row_bytes, size_t n_rows, int n_threads);
 
 /* 8.8 fixed-point taps cv.GaussianBlur uses for u8 images (n odd, <= GOFPID_MAX_KSIZE). */
 GOFPID_API int gofpid_gaussian_taps_q8(int n, double sigma, uint16_t *h_taps);

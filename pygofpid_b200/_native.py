@@ -94,6 +94,7 @@ SIGNATURES = {
     "gofpid_device_count": (ct.c_int, []),
     "gofpid_config_default": (None, [ct.POINTER(Config)]),
     "gofpid_host_alloc": (ct.c_int, [_sz, ct.c_int, ct.POINTER(_vp)]),
+    "gofpid_host_copy2d": (ct.c_int, [_vp, _sz, _vp, _sz, _sz, _sz, ct.c_int]),
     "gofpid_host_free": (ct.c_int, [_vp]),
     "gofpid_gaussian_taps_q8": (ct.c_int, [ct.c_int, ct.c_double, ct.POINTER(ct.c_uint16)]),
     "gofpid_pipeline_create": (ct.c_int, [ct.POINTER(Config), ct.c_int, ct.c_int, ct.c_int, ct.c_int,

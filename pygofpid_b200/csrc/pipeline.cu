@@ -1368,6 +1368,37 @@ GOFPID_API int gofpid_host_alloc(size_t bytes, int write_combined, void **out)
     }
     return GOFPID_OK;
 }
+GOFPID_API int gofpid_host_copy2d(void *dst, size_t dst_pitch, const void *src, size_t src_pitch, size_t row_bytes,
+                                  size_t n_rows, int n_threads)
+{
+    if ((!dst || !src) && row_bytes && n_rows) { set_error("null buffer"); return GOFPID_ERR_INVALID; }
+    if (n_rows > 1 && (dst_pitch < row_bytes || src_pitch < row_bytes)) {
+        set_error("pitch smaller than a row (%zu / %zu < %zu)", dst_pitch, src_pitch, row_bytes);
+        return GOFPID_ERR_INVALID;
+    }
+    if (!row_bytes || !n_rows) return GOFPID_OK;
+    static std::mutex mu;
+    static HostCopier *copier = nullptr;
+    static int copier_threads = -2;
+    std::lock_guard<std::mutex> lk(mu);
+    const unsigned hc = std::thread::hardware_concurrency();
+    int want = n_threads >= 0 ? n_threads : std::max(1, std::min(7, (int)hc / 2 - 1));
+    want = std::min(want, hc > 1 ? (int)hc - 1 : 0);
+    if (!copier || copier_threads != want) {
+        delete copier;
+        copier = new (std::nothrow) HostCopier(want, 500, true);
+        copier_threads = want;
+        if (!copier) { set_error("out of host memory"); return GOFPID_ERR_NOMEM; }
+    }
+    // (four strips, as the host entry points use them: a strip is reported once all its chunks are in place)
+    size_t next_row = 0;
+    bool in_order = true;
+    copier->copy2d(static_cast<uint8_t *>(dst), dst_pitch, static_cast<const uint8_t *>(src), src_pitch, row_bytes, n_rows, 4,
+                   [&](size_t r0, size_t nr) { in_order &= r0 == next_row; next_row = r0 + nr; });
+    if (!in_order || next_row != n_rows) { set_error("internal: strips reported out of order"); return GOFPID_ERR_INVALID; }
+    return GOFPID_OK;
+}
+
 GOFPID_API int gofpid_host_free(void *ptr)
 {
     if (ptr && cudaFreeHost(ptr) != cudaSuccess) { cudaGetLastError(); set_error("not a gofpid_host_alloc pointer"); return GOFPID_ERR_INVALID; }
