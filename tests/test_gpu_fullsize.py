@@ -170,3 +170,32 @@ def test_1080p_noise_without_morphology_through_the_dropin():
             assert np.array_equal(a["contour"], b["contour"]), t
             assert np.array_equal(a["center"], b["center"]) and np.array_equal(a["bottom"], b["bottom"]), t
         base = f
+
+
+# ----------------------------------------------------------------------------------------------
+# ... and the other end of the size range: frames smaller than one tile, one row, one pixel, through the
+# whole chain (blur, detector, open 3x3, blobs) against live cv2 -- frames alternate between a flat image and
+# noise, so nearly every pixel changes class every frame.
+@pytest.mark.parametrize("det", ["MOG2", "KNN", "FD"])
+@pytest.mark.parametrize("shape", [(1, 1), (1, 9), (3, 4), (7, 8, 3), (2, 8), (5, 3, 3), (9, 16), (4, 4, 3)])
+def test_tiny_frames_match_cv2(shape, det):
+    from pygofpid_b200 import HotPath
+    se = cv.getStructuringElement(cv.MORPH_RECT, (3, 3))
+    cv.setRNGSeed(7)
+    ref = cv_path.CvHotPath(frg_detect=det, mat_morph=[dict(fun=cv.erode, kernel=se), dict(fun=cv.dilate, kernel=se)],
+                            area_min=1.0)
+    hp = HotPath(shape, blur=("gaussian", (3, 3), 4.0), detector=det, morph=[("erode", se), ("dilate", se)],
+                 area_min=1.0, knn_seed=7, fd_threshold=5)
+    rng = np.random.default_rng(1)
+    for t in range(8):
+        f = rng.integers(0, 256, size=shape, dtype=np.uint8) if t % 2 else np.full(shape, 40, np.uint8)
+        want_mask, want_blobs = ref.step(f)
+        hp.process(f)
+        got_mask = hp.mask()
+        assert np.array_equal(got_mask, want_mask), (t, got_mask, want_mask)
+        got = hp.blobs()
+        assert len(got) == len(want_blobs), (t, len(got), len(want_blobs))
+        for g, w in zip(got, want_blobs):
+            assert np.array_equal(g["contour"], w["contour"]), t
+            assert np.array_equal(g["center"], w["center"]) and np.array_equal(g["bottom"], w["bottom"]), t
+    hp.close()
