@@ -202,6 +202,7 @@ private:
     }
     bool take_chunk()
     {
+        if (next_.load(std::memory_order_acquire) >= nchunks_) return false; // (a waiting caller polls this: no unbounded increments)
         const int c = next_.fetch_add(1, std::memory_order_acq_rel);
         if (c >= nchunks_) return false;
         const size_t r0 = (size_t)c * rows_per_chunk_, r1 = std::min(nrows_, r0 + rows_per_chunk_);
