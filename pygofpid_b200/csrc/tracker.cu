@@ -59,7 +59,10 @@ struct gofpid_tracker {
     std::vector<Track> tracks;
     int sys_already_in_alarm = 0;
     double duration = 0;
-    std::vector<double> dist; // scratch: n_blobs x n_tracks
+    // scratch of a step: one row of the distance matrix and what the distance needs from every track
+    std::vector<double> dist, a2, b2;
+    std::vector<int16_t> tcx, tcy;
+    std::vector<uint8_t> zero, col_neg;
     std::vector<BlobIn> blobs; // scratch
 };
 
@@ -86,19 +89,7 @@ int point_in_polygon(const std::vector<double> &poly, double px, double py)
     return inside ? 1 : -1;
 }
 
-// pipeline.py:659-689 for one (track, blob) pair
-double tracking_distance(const gofpid_tracker *t, const Track &tr, const BlobIn &b)
-{
-    const double height_min = t->persp_height[clip_row(t, tr.bottom[1])];
-    const int32_t rmaj = (int32_t)(height_min * t->factor);   // np.int32(...): truncation
-    const int32_t rmin = (int32_t)((double)rmaj / 2);
-    if (rmaj <= 0 || rmin <= 0) return 0;
-    const int16_t dx = (int16_t)(b.center[0] - tr.center[0]), dy = (int16_t)(b.center[1] - tr.center[1]);
-    const int16_t dx2 = (int16_t)((int)dx * (int)dx), dy2 = (int16_t)((int)dy * (int)dy); // int16 ** 2 wraps
-    const int32_t a2 = (int32_t)((uint32_t)rmaj * (uint32_t)rmaj), b2 = (int32_t)((uint32_t)rmin * (uint32_t)rmin);
-    return (double)dx2 / (double)a2 + (double)dy2 / (double)b2;
-}
-
+// (the distance of a (track, blob) pair, pipeline.py:659-689, is evaluated row by row in step())
 Track new_track(const BlobIn &b)
 {
     Track tr;
@@ -146,13 +137,35 @@ int step(gofpid_tracker *t, const BlobIn *blobs, int nb)
     } else if (nb == 0) {
         for (int j = nt - 1; j >= 0; j--) miss(t, j);
     } else {
-        t->dist.resize((size_t)nb * nt);
-        double *D = t->dist.data();
-        for (int i = 0; i < nb; i++)
-            for (int j = 0; j < nt; j++) D[(size_t)i * nt + j] = tracking_distance(t, T[j], blobs[i]);
+        // The reference fills an (n_blobs x n_tracks) matrix up front, walks the blobs (argmin of the blob's
+        // row; a pairing writes -1 into that one entry) and finally ages every track whose COLUMN has no
+        // negative / NaN entry.  Rows never see each other's -1, so the matrix is not kept: a row at a time
+        // over a structure-of-arrays snapshot of the tracks (pair() changes them while the blobs are walked)
+        // -- a plain loop the compiler vectorises -- plus one "column has a negative entry" flag per track.
+        t->dist.resize(nt); t->a2.resize(nt); t->b2.resize(nt); t->tcx.resize(nt); t->tcy.resize(nt);
+        t->zero.resize(nt); t->col_neg.assign(nt, 0);
+        double *row = t->dist.data(), *A2 = t->a2.data(), *B2 = t->b2.data();
+        int16_t *tcx = t->tcx.data(), *tcy = t->tcy.data();
+        uint8_t *zero = t->zero.data(), *col_neg = t->col_neg.data();
+        for (int j = 0; j < nt; j++) {
+            const double height_min = t->persp_height[clip_row(t, T[j].bottom[1])];
+            const int32_t rmaj = (int32_t)(height_min * t->factor);   // np.int32(...): truncation
+            const int32_t rmin = (int32_t)((double)rmaj / 2);
+            zero[j] = rmaj <= 0 || rmin <= 0;                          // the reference's distance is 0 there
+            A2[j] = zero[j] ? 1.0 : (double)(int32_t)((uint32_t)rmaj * (uint32_t)rmaj);
+            B2[j] = zero[j] ? 1.0 : (double)(int32_t)((uint32_t)rmin * (uint32_t)rmin);
+            tcx[j] = T[j].center[0]; tcy[j] = T[j].center[1];
+        }
         for (int i = 0; i < nb; i++) {
+            const int bcx = blobs[i].center[0], bcy = blobs[i].center[1];
+            for (int j = 0; j < nt; j++) { // tracking_distance(), int16 differences and squares wrapping as NumPy's do
+                const int16_t dx = (int16_t)(bcx - tcx[j]), dy = (int16_t)(bcy - tcy[j]);
+                const int16_t dx2 = (int16_t)((int)dx * (int)dx), dy2 = (int16_t)((int)dy * (int)dy);
+                const double d = (double)dx2 / A2[j] + (double)dy2 / B2[j];
+                row[j] = zero[j] ? 0.0 : d;
+            }
+            for (int j = 0; j < nt; j++) col_neg[j] |= (uint8_t)!(row[j] >= 0); // (a wrapped negative or a NaN entry)
             // np.argmin: first minimum; a NaN counts as the minimum
-            double *row = D + (size_t)i * nt;
             int jm = 0;
             if (!isnan(row[0]))
                 for (int j = 1; j < nt; j++) {
@@ -160,17 +173,14 @@ int step(gofpid_tracker *t, const BlobIn *blobs, int nb)
                     if (row[j] < row[jm]) jm = j;
                 }
             if (row[jm] <= 1) {
-                row[jm] = -1;
+                col_neg[jm] = 1; // (the -1 the reference writes)
                 pair(t, T[jm], blobs[i]);
             } else {
                 T.push_back(new_track(blobs[i])); // (T may reallocate: no reference into it is kept)
             }
         }
-        for (int j = nt - 1; j >= 0; j--) {
-            bool all_nonneg = true; // np.all(dist[:, j] >= 0): false for a paired (-1), a wrapped negative or a NaN entry
-            for (int i = 0; i < nb && all_nonneg; i++) all_nonneg = D[(size_t)i * nt + j] >= 0;
-            if (all_nonneg) miss(t, j);
-        }
+        for (int j = nt - 1; j >= 0; j--)
+            if (!col_neg[j]) miss(t, j); // np.all(dist[:, j] >= 0)
     }
     // ---- step 6: post-filter ---------------------------------------------------------------
     for (Track &tr : T) {
